@@ -1,0 +1,113 @@
+/* mtts.h -- C ABI of the B200-native CFM decoder (Matcha-TTS inference hot path).
+ *
+ * The reference (Lounes78/matcha-tts) has NO FFI/plugin layer: the path sits behind plain
+ * nn.Module methods.  This header is the boundary a maintainer binds instead of the PyTorch
+ * bodies of
+ *     Decoder.forward(x, mask, mu, t, spks, cond)                    reference model.py:964-1048
+ *     BASECFM.forward Euler / midpoint loop                          reference model.py:1084-1109
+ * (see INTEGRATION.md for the ctypes stub used by matcha_tts_b200/model.py).
+ *
+ * Conventions
+ *   - plain C, no torch types: device pointers + sizes + an opaque CUDA stream handle (cudaStream_t
+ *     passed as void*).  All tensors are contiguous fp32 in the reference's own layouts:
+ *     x / mu / out / z : (B, out_channels, T)   mask : (B, 1, T) as 0/1 floats   t : (B,)
+ *     spks : (B, in_channels - 2*out_channels) or NULL.
+ *   - the caller owns every buffer (weights arena, workspace, tensors); the library never
+ *     allocates device memory, never synchronises, and only enqueues work on the given stream.
+ *   - every function returns 0 on success or a negative MTTS_E* code; mtts_last_error() gives
+ *     the message of the last failure on the calling thread.  Shape violations are errors --
+ *     there is no silent fallback and no CPU path.
+ *   - one handle per (process, device); a handle is not thread-safe (neither is the reference).
+ */
+#ifndef MTTS_H_
+#define MTTS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTTS_OK 0
+#define MTTS_EINVAL (-1)   /* bad argument / unsupported shape */
+#define MTTS_ECUDA (-2)    /* a CUDA runtime / driver call failed */
+#define MTTS_ESTATE (-3)   /* call order violated (weights not loaded, arena not set, ...) */
+#define MTTS_ENOMEM (-4)   /* caller-provided buffer too small */
+
+#define MTTS_SOLVER_EULER 0
+#define MTTS_SOLVER_MIDPOINT 1
+
+typedef struct MttsHandle MttsHandle;
+
+/* Hyper-parameters of the estimator; mirrors Decoder.__init__ (reference model.py:835-962) for the
+ * architecture the reference instantiates (main.py:63-79): two U-Net levels of `channels` width,
+ * one transformer block per stage, SnakeBeta feed-forward, GroupNorm(8).
+ * Supported: channels == 256, heads == 2, head_dim == 64, out_channels == 80,
+ * in_channels in {160 .. 256} and a multiple of 16 (160 = LJSpeech, 224 = multi-speaker). */
+typedef struct MttsConfig {
+  int in_channels;
+  int out_channels;
+  int channels;
+  int heads;
+  int head_dim;
+  int n_mid_blocks;
+} MttsConfig;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out);
+void mtts_destroy(MttsHandle* h);
+const char* mtts_last_error(void);
+const char* mtts_version(void);
+
+/* ---- weights: replaces nn.Module.load_state_dict for `decoder.estimator.*` (model.py App. B keys,
+ * checkpoint load at reference main.py:94-121).  The table lists every state-dict key the estimator
+ * owns, in a fixed order; entries whose name starts with '@' are host-derived constants
+ * ("@time_freqs": exp(arange(C/2) * -ln(1e4)/(C/2-1)), reference model.py:757-758).
+ * mtts_load_weight() converts one fp32 tensor in the reference's layout into the packed fp16/fp32
+ * kernel layouts inside the caller-provided arena. */
+int mtts_num_weights(const MttsHandle* h);
+const char* mtts_weight_name(const MttsHandle* h, int idx);
+int64_t mtts_weight_numel(const MttsHandle* h, int idx);
+size_t mtts_weight_arena_bytes(const MttsHandle* h);
+int mtts_set_weight_arena(MttsHandle* h, void* dev_arena, size_t bytes, void* stream);
+int mtts_load_weight(MttsHandle* h, int idx, const float* dev_src, int64_t numel, void* stream);
+int mtts_weights_loaded(const MttsHandle* h); /* 1 when every table entry has been loaded */
+
+/* ---- workspace ----------------------------------------------------------------------------- */
+/* Bytes of scratch needed for a batch of B utterances padded to T frames (T even, T >= 2).
+ * Returns 0 on invalid shapes. */
+size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T);
+
+/* ---- compute ------------------------------------------------------------------------------- */
+/* One estimator call: out = Decoder.forward(x, mask, mu, t, spks)     (reference model.py:964) */
+int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const float* mask, const float* t,
+                           const float* spks, float* out, void* workspace, size_t workspace_bytes, int B, int T,
+                           void* stream);
+
+/* The ODE solve of BASECFM.forward (reference model.py:1086-1104) on a caller-provided initial
+ * state: z <- z + dt * v(z, i/n) for i < n (Euler), or the midpoint rule.  z_inout holds z_0 =
+ * randn * temperature on entry (drawn by the host exactly like model.py:1085) and z_n on return.
+ * use_graph != 0 captures the whole solve into a CUDA graph (cached per shape/pointers). */
+int mtts_euler_solve(MttsHandle* h, float* z_inout, const float* mu, const float* mask, const float* spks,
+                     int n_timesteps, int solver, void* workspace, size_t workspace_bytes, int B, int T,
+                     int use_graph, void* stream);
+
+/* Number of kernels enqueued by the last estimator_forward / euler_solve call on this handle. */
+int mtts_last_launch_count(const MttsHandle* h);
+
+/* ---- introspection used by the parity tests -------------------------------------------------- */
+/* Stop the estimator after `n` kernel launches (n < 0: run everything). */
+int mtts_debug_set_launch_limit(MttsHandle* h, int n);
+/* Byte offset / row count / column count of a named intermediate inside the workspace for (B, T);
+ * level 0 = T frames, 1 = T/2 frames.  Returns -1 for an unknown name. */
+int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, const char* name);
+/* Generic implicit-GEMM entry for unit tests: out[r, n] = bias[n] + sum_taps A[r + shift_i, :] . W[n, i*C:(i+1)*C]
+ * A: (rows, C) fp16, W: (N, ntaps*C) fp16, out: (rows, N) fp16; C % 64 == 0, N % 128 == 0. */
+int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
+                    int ntaps, const int* shifts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTTS_H_ */

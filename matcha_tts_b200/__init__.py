@@ -1,0 +1,10 @@
+"""matcha_tts_b200 -- B200-native CFM decoder (Matcha-TTS inference hot path).
+
+Package name note: the task names the package `matcha-tts_b200`; a hyphen is not importable in
+Python, so the directory is `matcha_tts_b200`.
+"""
+from .model import (BASECFM, CFM, Decoder, MatchaTTS, denormalize, fix_len_compatibility, generate_path,
+                    sequence_mask)
+
+__all__ = ["BASECFM", "CFM", "Decoder", "MatchaTTS", "denormalize", "fix_len_compatibility", "generate_path",
+           "sequence_mask"]

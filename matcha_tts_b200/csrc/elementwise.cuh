@@ -1,0 +1,256 @@
+// Bandwidth-bound kernels around the GEMMs: mask/row-map preparation, the first conv's operand
+// buffer, GroupNorm-apply + Mish (+time embedding, +residual, +LayerNorm), the data-independent
+// time-embedding path, and weight packing.  All activations are channels-last fp16 in the flat
+// row space described in gemm_tc.cuh; every thread block handles rows of ONE utterance so the
+// GroupNorm statistics (which span all frames of an utterance, padded ones included -- reference
+// model.py:769) are finalised once per block from the deterministic partial sums.
+#pragma once
+#include "ptx.cuh"
+
+namespace mtts {
+
+// ---------------------------------------------------------------------------------------------
+// mask (B,T) float -> flat per-row masks / utterance ids for both U-Net levels, masked-key counts
+// level T : row b*(T+2)+t, guard rows t in {T, T+1};  level H = T/2: row b*(H+1)+m, guard row m = H,
+// mask_H[b,m] = mask[b, 2m]  (reference model.py:1003  mask_down[:, :, ::2])
+// ---------------------------------------------------------------------------------------------
+__global__ void mask_prep_kernel(const float* __restrict__ mask, int T, float* __restrict__ mT,
+                                 float* __restrict__ mH, int* __restrict__ rowbT, int* __restrict__ rowbH,
+                                 int* __restrict__ npadT, int* __restrict__ npadH) {
+  const int b = blockIdx.x, H = T / 2, LpT = T + 2, LpH = H + 1;
+  __shared__ int cT, cH;
+  if (threadIdx.x == 0) { cT = 0; cH = 0; }
+  __syncthreads();
+  int nT = 0, nH = 0;
+  for (int t = threadIdx.x; t < LpT; t += blockDim.x) {
+    float m = (t < T) ? mask[(size_t)b * T + t] : 0.f;
+    mT[(size_t)b * LpT + t] = m;
+    rowbT[(size_t)b * LpT + t] = (t < T) ? b : -1;
+    if (t < T && m == 0.f) ++nT;
+  }
+  for (int t = threadIdx.x; t < LpH; t += blockDim.x) {
+    float m = (t < H) ? mask[(size_t)b * T + 2 * t] : 0.f;
+    mH[(size_t)b * LpH + t] = m;
+    rowbH[(size_t)b * LpH + t] = (t < H) ? b : -1;
+    if (t < H && m == 0.f) ++nH;
+  }
+  atomicAdd(&cT, nT);
+  atomicAdd(&cH, nH);
+  __syncthreads();
+  if (threadIdx.x == 0) { npadT[b] = cT; npadH[b] = cH; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// X0[row][c] = fp16( cat[z, mu, spks][b, c, t] * mask[b,t] ), zero pad channels and guard rows
+// (reference model.py:975-979 cat + the x*mask of Block1D / res_conv, :774, :789)
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_x0_kernel(const float* __restrict__ z, const float* __restrict__ mu,
+                               const float* __restrict__ spks, const float* __restrict__ mT, int T, int nf,
+                               int nspk, int cinp, __half* __restrict__ x0, int z_only) {
+  extern __shared__ float tile[];  // [cinp][33]
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, LpT = T + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int t = t0 + lane;
+  const float m = (t < T) ? mT[(size_t)b * LpT + t] : 0.f;
+  const int cend = z_only ? nf : cinp;
+  for (int c = warp; c < cend; c += nw) {
+    float v = 0.f;
+    if (t < T) {
+      if (c < nf) v = z[((size_t)b * nf + c) * T + t];
+      else if (c < 2 * nf) v = mu[((size_t)b * nf + (c - nf)) * T + t];
+      else if (c < 2 * nf + nspk) v = spks[(size_t)b * nspk + (c - 2 * nf)];
+    }
+    tile[c * 33 + lane] = v * m;
+  }
+  __syncthreads();
+  const int npairs = cend / 2;
+  for (int i = threadIdx.x; i < 32 * npairs; i += blockDim.x) {
+    const int tl = i / npairs, cp = i % npairs;
+    if (t0 + tl < LpT) {
+      __half2 hv = __floats2half2_rn(tile[(2 * cp) * 33 + tl], tile[(2 * cp + 1) * 33 + tl]);
+      *reinterpret_cast<__half2*>(x0 + ((size_t)b * LpT + t0 + tl) * cinp + 2 * cp) = hv;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(8, 256) apply + Mish + mask, fused with what follows it in the reference:
+//   MODE 0 (Block1D #1 of a ResnetBlock1D, and final_block):
+//        h = (Mish(GN(y)) * m + temb[c]) * m                      model.py:773-775, :786-787
+//   MODE 1 (Block1D #2):  x_r = Mish(GN(y)) * m + res  (NOT masked, :788-789),  a = LayerNorm1(x_r) :735
+// y is the raw conv output (+bias) in fp16; statistics come from the conv epilogue's partial sums.
+// grid = (ceil(Lp/64), B), block = 256 (8 warps, one row per warp per iteration, 8 channels per lane)
+// ---------------------------------------------------------------------------------------------
+struct GnParams {
+  const __half* y;
+  const float* stats_part;  // [B][S][16] (sum, sumsq) per group
+  int S, L, Lp;
+  const float* gamma;
+  const float* beta;
+  const float* rowmask;
+  const float* temb;  // [n_t][256] or null
+  int t_off, t_stride, t_ld;  // temb row = t_off + b*t_stride, row pitch t_ld floats
+  __half* out;        // MODE 0: h ; MODE 1: x_r
+  const __half* res;  // MODE 1
+  const float* ln_g;
+  const float* ln_b;
+  __half* out2;  // MODE 1: a
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
+  __shared__ float s_mean[8], s_rstd[8];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 8) {
+    const int g = threadIdx.x;
+    const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
+    double s = 0.0, ss = 0.0;
+    for (int sl = 0; sl <= last - first; ++sl) {
+      const float* pp = p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * g;
+      s += (double)pp[0];
+      ss += (double)pp[1];
+    }
+    const double n = 32.0 * (double)p.L;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int c0 = lane * 8, g = lane >> 2;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float ga[8], be[8], te[8], lg[8], lb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = p.gamma[c0 + j] * rstd;
+    be[j] = p.beta[c0 + j] - mean * ga[j];
+    te[j] = (MODE == 0 && p.temb) ? p.temb[(size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0 + j] : 0.f;
+    if (MODE == 1) { lg[j] = p.ln_g[c0 + j]; lb[j] = p.ln_b[c0 + j]; }
+  }
+  const int tend = min(p.Lp, (int)(blockIdx.x + 1) * 64);
+  for (int t = blockIdx.x * 64 + warp; t < tend; t += 8) {
+    const size_t row = (size_t)b * p.Lp + t;
+    uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
+    if (t < p.L) {
+      const float m = p.rowmask[row];
+      const uint4 yv = *reinterpret_cast<const uint4*>(p.y + row * 256 + c0);
+      float v[8];
+      float2 f;
+      f = unpack_h2(yv.x); v[0] = f.x; v[1] = f.y;
+      f = unpack_h2(yv.y); v[2] = f.x; v[3] = f.y;
+      f = unpack_h2(yv.z); v[4] = f.x; v[5] = f.y;
+      f = unpack_h2(yv.w); v[6] = f.x; v[7] = f.y;
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m + te[j]) * m;
+      } else {
+        const uint4 rv = *reinterpret_cast<const uint4*>(p.res + row * 256 + c0);
+        float r[8];
+        f = unpack_h2(rv.x); r[0] = f.x; r[1] = f.y;
+        f = unpack_h2(rv.y); r[2] = f.x; r[3] = f.y;
+        f = unpack_h2(rv.z); r[4] = f.x; r[5] = f.y;
+        f = unpack_h2(rv.w); r[6] = f.x; r[7] = f.y;
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m + r[j];
+          s += v[j];
+          ss = fmaf(v[j], v[j], ss);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, off);
+          ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        }
+        const float lmean = s * (1.f / 256.f);
+        const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
+        o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
+      }
+      o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+    *reinterpret_cast<uint4*>(p.out + row * 256 + c0) = o;  // guard rows are written as zeros
+    if (MODE == 1) *reinterpret_cast<uint4*>(p.out2 + row * 256 + c0) = o2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// time path (data independent, reference model.py:753-762, :828-832, :780)
+// ---------------------------------------------------------------------------------------------
+// t values of the fixed-step solver: t_i = i/n in double, rounded to fp32 like the reference's
+// torch.tensor([i / n_timesteps]) (:1091); midpoint adds fp32(dt)*0.5 in fp32 (:1101).
+__global__ void solver_times_kernel(float* __restrict__ tv, int n, int midpoint) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)((double)i / (double)n);
+  if (!midpoint) {
+    tv[i] = t;
+  } else {
+    const float dt = (float)(1.0 / (double)n);
+    tv[2 * i] = t;
+    tv[2 * i + 1] = t + dt * 0.5f;
+  }
+}
+// e[i][j] = sin(1000 t_i w_j), e[i][half+j] = cos(1000 t_i w_j); w_j supplied by the host exactly
+// as the reference computes it.
+__global__ void sinus_emb_kernel(const float* __restrict__ tv, const float* __restrict__ freqs, int n_t, int half,
+                                 float* __restrict__ e) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_t * half) return;
+  const int i = idx / half, j = idx % half;
+  const float arg = (1000.f * tv[i]) * freqs[j];
+  e[(size_t)i * 2 * half + j] = sinf(arg);
+  e[(size_t)i * 2 * half + half + j] = cosf(arg);
+}
+// out[i][n] = act( b[n] + sum_k W[n][k] in[i][k] ), one warp per output feature, fp32.
+// act: 0 none, 1 SiLU, 2 Mish
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int n_t, int K, int N, int act) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float w[32];  // K <= 1024
+#pragma unroll
+  for (int j = 0; j < 32; ++j) w[j] = (lane + 32 * j < K) ? W[(size_t)n * K + lane + 32 * j] : 0.f;
+  for (int i = 0; i < n_t; ++i) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (lane + 32 * j < K) acc = fmaf(w[j], in[(size_t)i * K + lane + 32 * j], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      float v = acc + bias[n];
+      if (act == 1) v = v / (1.f + expf(-v));
+      else if (act == 2) v = v * tanhf(v > 20.f ? v : log1pf(expf(v)));
+      out[(size_t)i * N + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (once, at load time)
+// ---------------------------------------------------------------------------------------------
+// dst[(n + n_off)*ldd + k_off + c] = fp16(scale * src[n*sn + c*sc + off])
+__global__ void pack2d_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int C, long sn, long sc,
+                              long off, int n_off, int ldd, int k_off, float scale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * C) return;
+  const int n = (int)(i / C), c = (int)(i % C);
+  dst[(size_t)(n + n_off) * ldd + k_off + c] = __float2half_rn(scale * src[n * sn + c * sc + off]);
+}
+// mode 0: copy; 1: exp(x); 2: 1/(exp(x)+1e-9)
+__global__ void packf_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int mode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = src[i];
+  if (mode == 1) v = expf(v);
+  else if (mode == 2) v = 1.0f / (expf(v) + 1e-9f);
+  dst[i] = v;
+}
+
+}  // namespace mtts

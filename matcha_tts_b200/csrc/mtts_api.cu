@@ -1,0 +1,882 @@
+// C-ABI implementation (include/mtts.h): weight packing, workspace planning, TMA tensor maps,
+// and the launch sequence of one estimator call / the whole ODE solve.
+// Host logic only enqueues kernels on the caller's stream; no device allocation, no sync.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mtts.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+using namespace mtts;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(MTTS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps (driver entry point fetched at run time: the .so has no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int init_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return fail(MTTS_ECUDA, "cuTensorMapEncodeTiled entry point not available (needs an NVIDIA driver)");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+// fp16 2-D row-major [rows, cols] with row pitch `pitch` elements; box = (64 cols, box_rows), 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows);
+    return fail(MTTS_ECUDA, buf);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct PackOp {
+  int kind;  // 0: fp32 -> fp16 strided 2-D pack, 1: fp32 copy (mode 0/1/2)
+  size_t dst;  // byte offset in the arena
+  int N, C;
+  long sn, sc, off;
+  int n_off, ldd, k_off;
+  float scale;
+  int mode;
+};
+struct WEntry {
+  std::string name;
+  int64_t numel;
+  std::vector<PackOp> ops;
+  bool loaded = false;
+};
+
+struct StageW {
+  int nsrc;
+  int src_cols[2];  // padded columns of each input source
+  size_t c1, c2, res, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets)
+  size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
+  CUtensorMap m_c1, m_c2, m_res, m_qkv, m_wo, m_ff1, m_ff2;
+};
+
+struct WsLayout {
+  int B, T, H, LpT, LpH, rowsT, rowsH, LpadT, LpadH, S, cinp, nt_max;
+  size_t maskT, maskH, rowbT, rowbH, npadT, npadH, tvals, te_e, te_h1, te_h2, te6, part;
+  size_t x0, y, res, h1, xr, a, xa, q, k, o, vt, s;
+  size_t skip0, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF, zmid;
+  size_t vt_bytes, total;
+};
+
+struct LevelMaps {
+  CUtensorMap h1, a, o, s, q, k, vt;
+};
+struct Plan {
+  WsLayout w;
+  char* ws;
+  LevelMaps lv[2];
+  CUtensorMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
+};
+
+struct GraphKey {
+  const void *z, *mu, *mask, *spks, *ws;
+  int B, T, n, solver;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(z, mu, mask, spks, ws, B, T, n, solver) <
+           std::tie(o.z, o.mu, o.mask, o.spks, o.ws, o.B, o.T, o.n, o.solver);
+  }
+};
+
+struct MttsHandle {
+  MttsConfig cfg;
+  int device, num_sms;
+  int cinp, nspk;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<WEntry> entries;
+  StageW st[6];
+  // non-stage weights
+  size_t freqs, tw1, tb1, tw2, tb2, mlpW, mlpB;
+  size_t w_down0, w_down1, w_up0, w_up1, w_fin, w_proj;
+  size_t b_down0, b_down1, b_up0, b_up1, b_fin, gnf_g, gnf_b, b_proj;
+  CUtensorMap m_down0, m_down1, m_up0, m_up1, m_fin, m_proj;
+  bool maps_ready = false;
+  std::map<std::tuple<const void*, int, int>, Plan> plans;
+  std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
+  int launch_count = 0, launch_limit = -1;
+};
+
+static const char* kStageNames[6] = {"down_blocks.0", "down_blocks.1", "mid_blocks.0",
+                                     "mid_blocks.1",  "up_blocks.0",   "up_blocks.1"};
+
+// ------------------------------------------------------------------------------------------------
+// arena layout + weight table
+// ------------------------------------------------------------------------------------------------
+static PackOp op_h(size_t dst, int N, int C, long sn, long sc, long off, int n_off, int ldd, int k_off,
+                   float scale = 1.f) {
+  PackOp o{};
+  o.kind = 0; o.dst = dst; o.N = N; o.C = C; o.sn = sn; o.sc = sc; o.off = off;
+  o.n_off = n_off; o.ldd = ldd; o.k_off = k_off; o.scale = scale;
+  return o;
+}
+static PackOp op_f(size_t dst, int n, int mode = 0) {
+  PackOp o{};
+  o.kind = 1; o.dst = dst; o.N = n; o.mode = mode;
+  return o;
+}
+
+static void build_tables(MttsHandle* h) {
+  const int C = h->cfg.channels, Cin = h->cfg.in_channels, TD = 4 * C, FD = 4 * C, AD = h->cfg.heads * h->cfg.head_dim;
+  size_t cur = 0;
+  auto alloc = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  auto add = [&](const std::string& name, int64_t numel, std::vector<PackOp> ops) {
+    WEntry e; e.name = name; e.numel = numel; e.ops = std::move(ops);
+    h->entries.push_back(std::move(e));
+  };
+  // conv k3 weight (N, Ci, 3) -> [N, 3*CiTot] tap-major
+  auto conv3_ops = [&](size_t dst, int N, int Ci, int CiTot) {
+    std::vector<PackOp> v;
+    for (int t = 0; t < 3; ++t) v.push_back(op_h(dst, N, Ci, (long)Ci * 3, 3, t, 0, 3 * CiTot, t * CiTot));
+    return v;
+  };
+
+  h->freqs = alloc(sizeof(float) * (Cin / 2));
+  add("@time_freqs", Cin / 2, {op_f(h->freqs, Cin / 2)});
+  h->tw1 = alloc(sizeof(float) * TD * Cin); h->tb1 = alloc(sizeof(float) * TD);
+  h->tw2 = alloc(sizeof(float) * TD * TD);  h->tb2 = alloc(sizeof(float) * TD);
+  h->mlpW = alloc(sizeof(float) * 6 * C * TD); h->mlpB = alloc(sizeof(float) * 6 * C);
+  add("time_mlp.linear_1.weight", (int64_t)TD * Cin, {op_f(h->tw1, TD * Cin)});
+  add("time_mlp.linear_1.bias", TD, {op_f(h->tb1, TD)});
+  add("time_mlp.linear_2.weight", (int64_t)TD * TD, {op_f(h->tw2, TD * TD)});
+  add("time_mlp.linear_2.bias", TD, {op_f(h->tb2, TD)});
+
+  for (int s = 0; s < 6; ++s) {
+    StageW& w = h->st[s];
+    int ci_real, ci_tot;
+    if (s == 0) { w.nsrc = 1; w.src_cols[0] = h->cinp; w.src_cols[1] = 0; ci_real = Cin; ci_tot = h->cinp; }
+    else if (s < 4) { w.nsrc = 1; w.src_cols[0] = C; w.src_cols[1] = 0; ci_real = C; ci_tot = C; }
+    else { w.nsrc = 2; w.src_cols[0] = C; w.src_cols[1] = C; ci_real = 2 * C; ci_tot = 2 * C; }
+    w.c1 = alloc(2ull * C * 3 * ci_tot); w.c2 = alloc(2ull * C * 3 * C); w.res = alloc(2ull * C * ci_tot);
+    w.qkv = alloc(2ull * 3 * AD * C); w.wo = alloc(2ull * C * AD);
+    w.ff1 = alloc(2ull * FD * C); w.ff2 = alloc(2ull * C * FD);
+    size_t* f256[] = {&w.c1_b, &w.gn1_g, &w.gn1_b, &w.c2_b, &w.gn2_g, &w.gn2_b, &w.res_b, &w.ln1_g,
+                      &w.ln1_b, &w.o_b,  &w.ln3_g, &w.ln3_b, &w.ff2_b};
+    for (size_t* p : f256) *p = alloc(sizeof(float) * C);
+    w.ff1_b = alloc(sizeof(float) * FD); w.sn_a = alloc(sizeof(float) * FD); w.sn_ib = alloc(sizeof(float) * FD);
+
+    const std::string r = std::string(kStageNames[s]) + ".0", t = std::string(kStageNames[s]) + ".1.0";
+    add(r + ".mlp.1.weight", (int64_t)C * TD, {op_f(h->mlpW + sizeof(float) * (size_t)s * C * TD, C * TD)});
+    add(r + ".mlp.1.bias", C, {op_f(h->mlpB + sizeof(float) * (size_t)s * C, C)});
+    add(r + ".block1.block.0.weight", (int64_t)C * ci_real * 3, conv3_ops(w.c1, C, ci_real, ci_tot));
+    add(r + ".block1.block.0.bias", C, {op_f(w.c1_b, C)});
+    add(r + ".block1.block.1.weight", C, {op_f(w.gn1_g, C)});
+    add(r + ".block1.block.1.bias", C, {op_f(w.gn1_b, C)});
+    add(r + ".block2.block.0.weight", (int64_t)C * C * 3, conv3_ops(w.c2, C, C, C));
+    add(r + ".block2.block.0.bias", C, {op_f(w.c2_b, C)});
+    add(r + ".block2.block.1.weight", C, {op_f(w.gn2_g, C)});
+    add(r + ".block2.block.1.bias", C, {op_f(w.gn2_b, C)});
+    add(r + ".res_conv.weight", (int64_t)C * ci_real, {op_h(w.res, C, ci_real, ci_real, 1, 0, 0, ci_tot, 0)});
+    add(r + ".res_conv.bias", C, {op_f(w.res_b, C)});
+    add(t + ".norm1.weight", C, {op_f(w.ln1_g, C)});
+    add(t + ".norm1.bias", C, {op_f(w.ln1_b, C)});
+    // softmax scale head_dim^-0.5 folded into to_q (exact: power of two)
+    const float qs = 1.0f / sqrtf((float)h->cfg.head_dim);
+    add(t + ".attn1.to_q.weight", (int64_t)AD * C, {op_h(w.qkv, AD, C, C, 1, 0, 0, C, 0, qs)});
+    add(t + ".attn1.to_k.weight", (int64_t)AD * C, {op_h(w.qkv, AD, C, C, 1, 0, AD, C, 0)});
+    add(t + ".attn1.to_v.weight", (int64_t)AD * C, {op_h(w.qkv, AD, C, C, 1, 0, 2 * AD, C, 0)});
+    add(t + ".attn1.to_out.0.weight", (int64_t)C * AD, {op_h(w.wo, C, AD, AD, 1, 0, 0, AD, 0)});
+    add(t + ".attn1.to_out.0.bias", C, {op_f(w.o_b, C)});
+    add(t + ".norm3.weight", C, {op_f(w.ln3_g, C)});
+    add(t + ".norm3.bias", C, {op_f(w.ln3_b, C)});
+    add(t + ".ff.net.0.alpha", FD, {op_f(w.sn_a, FD, 1)});
+    add(t + ".ff.net.0.beta", FD, {op_f(w.sn_ib, FD, 2)});
+    add(t + ".ff.net.0.proj.weight", (int64_t)FD * C, {op_h(w.ff1, FD, C, C, 1, 0, 0, C, 0)});
+    add(t + ".ff.net.0.proj.bias", FD, {op_f(w.ff1_b, FD)});
+    add(t + ".ff.net.2.weight", (int64_t)C * FD, {op_h(w.ff2, C, FD, FD, 1, 0, 0, FD, 0)});
+    add(t + ".ff.net.2.bias", C, {op_f(w.ff2_b, C)});
+  }
+  h->w_down0 = alloc(2ull * C * 3 * C); h->w_down1 = alloc(2ull * C * 3 * C);
+  h->w_up0 = alloc(2ull * 2 * C * 3 * C); h->w_up1 = alloc(2ull * C * 3 * C);
+  h->w_fin = alloc(2ull * C * 3 * C); h->w_proj = alloc(2ull * 128 * C);
+  h->b_down0 = alloc(sizeof(float) * C); h->b_down1 = alloc(sizeof(float) * C);
+  h->b_up0 = alloc(sizeof(float) * 2 * C); h->b_up1 = alloc(sizeof(float) * C);
+  h->b_fin = alloc(sizeof(float) * C); h->gnf_g = alloc(sizeof(float) * C); h->gnf_b = alloc(sizeof(float) * C);
+  h->b_proj = alloc(sizeof(float) * 128);
+  add("down_blocks.0.2.conv.weight", (int64_t)C * C * 3, conv3_ops(h->w_down0, C, C, C));
+  add("down_blocks.0.2.conv.bias", C, {op_f(h->b_down0, C)});
+  add("down_blocks.1.2.weight", (int64_t)C * C * 3, conv3_ops(h->w_down1, C, C, C));
+  add("down_blocks.1.2.bias", C, {op_f(h->b_down1, C)});
+  // ConvTranspose1d k4 s2 p1, weight (in, out, k):  out[2r] = W1^T x[r] + W3^T x[r-1];
+  // out[2r+1] = W0^T x[r+1] + W2^T x[r].  Packed [512, 3*C]: K blocks = taps (r-1, r, r+1),
+  // rows [0,C) = even outputs, rows [C,2C) = odd outputs; unused blocks stay zero.
+  add("up_blocks.0.2.conv.weight", (int64_t)C * C * 4,
+      {op_h(h->w_up0, C, C, 4, (long)C * 4, 3, 0, 3 * C, 0), op_h(h->w_up0, C, C, 4, (long)C * 4, 1, 0, 3 * C, C),
+       op_h(h->w_up0, C, C, 4, (long)C * 4, 2, C, 3 * C, C), op_h(h->w_up0, C, C, 4, (long)C * 4, 0, C, 3 * C, 2 * C)});
+  add("up_blocks.0.2.conv.bias", C, {op_f(h->b_up0, C), op_f(h->b_up0 + sizeof(float) * C, C)});
+  add("up_blocks.1.2.weight", (int64_t)C * C * 3, conv3_ops(h->w_up1, C, C, C));
+  add("up_blocks.1.2.bias", C, {op_f(h->b_up1, C)});
+  add("final_block.block.0.weight", (int64_t)C * C * 3, conv3_ops(h->w_fin, C, C, C));
+  add("final_block.block.0.bias", C, {op_f(h->b_fin, C)});
+  add("final_block.block.1.weight", C, {op_f(h->gnf_g, C)});
+  add("final_block.block.1.bias", C, {op_f(h->gnf_b, C)});
+  const int NO = h->cfg.out_channels;
+  add("final_proj.weight", (int64_t)NO * C, {op_h(h->w_proj, NO, C, C, 1, 0, 0, C, 0)});
+  add("final_proj.bias", NO, {op_f(h->b_proj, NO)});
+  h->arena_bytes = cur;
+}
+
+static int build_weight_maps(MttsHandle* h) {
+  if (int e = init_encode()) return e;
+  const int C = h->cfg.channels;
+  char* a = h->arena;
+  for (int s = 0; s < 6; ++s) {
+    StageW& w = h->st[s];
+    const int ci = w.src_cols[0] + w.src_cols[1];
+    if (make_map(&w.m_c1, a + w.c1, C, 3 * ci, 3 * ci, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_c2, a + w.c2, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_res, a + w.res, C, ci, ci, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_qkv, a + w.qkv, 384, C, C, 128)) return MTTS_ECUDA;
+    if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_ff2, a + w.ff2, C, 4 * C, 4 * C, 256)) return MTTS_ECUDA;
+  }
+  if (make_map(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_map(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_map(&h->m_up0, a + h->w_up0, 2 * C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_map(&h->m_up1, a + h->w_up1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_map(&h->m_fin, a + h->w_fin, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_map(&h->m_proj, a + h->w_proj, 128, C, C, 128)) return MTTS_ECUDA;
+  h->maps_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+static const int kMaxTimes = 2048;  // rows of the time-embedding table (>= B and >= 2*n_timesteps)
+
+static bool ws_layout(const MttsHandle* h, int B, int T, WsLayout* w) {
+  if (B < 1 || T < 2 || (T & 1) || B > kMaxTimes) return false;
+  memset(w, 0, sizeof *w);
+  const int C = h->cfg.channels, NF = h->cfg.out_channels;
+  w->B = B; w->T = T; w->H = T / 2; w->LpT = T + 2; w->LpH = T / 2 + 1;
+  w->rowsT = B * w->LpT; w->rowsH = B * w->LpH;
+  w->LpadT = (int)align_up(T, 8); w->LpadH = (int)align_up(T / 2, 8);
+  w->S = (T + 31) / 32 + 1;
+  w->cinp = h->cinp; w->nt_max = kMaxTimes;
+  size_t cur = 0;
+  auto alloc = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 1024); return o; };
+  const size_t rT = w->rowsT, rH = w->rowsH;
+  w->maskT = alloc(4 * rT); w->maskH = alloc(4 * rH); w->rowbT = alloc(4 * rT); w->rowbH = alloc(4 * rH);
+  w->npadT = alloc(4 * B); w->npadH = alloc(4 * B);
+  w->tvals = alloc(4 * kMaxTimes); w->te_e = alloc(4ull * kMaxTimes * h->cfg.in_channels);
+  w->te_h1 = alloc(4ull * kMaxTimes * 4 * C); w->te_h2 = alloc(4ull * kMaxTimes * 4 * C);
+  w->te6 = alloc(4ull * kMaxTimes * 6 * C);
+  w->part = alloc(4ull * B * w->S * 16);
+  w->x0 = alloc(2 * rT * w->cinp);
+  w->y = alloc(2 * rT * C); w->res = alloc(2 * rT * C); w->h1 = alloc(2 * rT * C); w->xr = alloc(2 * rT * C);
+  w->a = alloc(2 * rT * C); w->xa = alloc(2 * rT * C);
+  w->q = alloc(2 * rT * 128); w->k = alloc(2 * rT * 128); w->o = alloc(2 * rT * 128);
+  w->vt_bytes = 2ull * B * 128 * w->LpadT;
+  w->vt = alloc(w->vt_bytes);
+  w->s = alloc(2 * rT * 4 * C);
+  w->skip0 = alloc(2 * rT * C); w->xD0 = alloc(2 * rH * C); w->skip1 = alloc(2 * rH * C); w->xD1 = alloc(2 * rH * C);
+  w->xM0 = alloc(2 * rH * C); w->xM1 = alloc(2 * rH * C); w->xU0s = alloc(2 * rH * C);
+  w->xU0 = alloc(2 * rT * C); w->xU1s = alloc(2 * rT * C); w->xF = alloc(2 * rT * C);
+  w->zmid = alloc(4ull * B * NF * T);
+  w->total = cur;
+  return true;
+}
+
+static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cudaStream_t stream, Plan** out) {
+  auto key = std::make_tuple((const void*)ws, B, T);
+  auto it = h->plans.find(key);
+  if (it != h->plans.end()) { *out = &it->second; return 0; }
+  Plan P;
+  if (!ws_layout(h, B, T, &P.w)) return fail(MTTS_EINVAL, "unsupported shape: need B >= 1, T even and >= 2");
+  if (ws_bytes < P.w.total) return fail(MTTS_ENOMEM, "workspace too small (see mtts_workspace_bytes)");
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(MTTS_EINVAL, "workspace must be 1024-byte aligned");
+  if (int e = init_encode()) return e;
+  P.ws = static_cast<char*>(ws);
+  const WsLayout& w = P.w;
+  const int C = h->cfg.channels;
+  char* b = P.ws;
+  for (int lv = 0; lv < 2; ++lv) {
+    const uint64_t rows = lv ? w.rowsH : w.rowsT;
+    const int Lpad = lv ? w.LpadH : w.LpadT;
+    LevelMaps& m = P.lv[lv];
+    if (make_map(&m.h1, b + w.h1, rows, C, C, 128)) return MTTS_ECUDA;
+    if (make_map(&m.a, b + w.a, rows, C, C, 128)) return MTTS_ECUDA;
+    if (make_map(&m.o, b + w.o, rows, 128, 128, 128)) return MTTS_ECUDA;
+    if (make_map(&m.s, b + w.s, rows, 4 * C, 4 * C, 128)) return MTTS_ECUDA;
+    if (make_map(&m.q, b + w.q, rows, 128, 128, 128)) return MTTS_ECUDA;
+    if (make_map(&m.k, b + w.k, rows, 128, 128, 128)) return MTTS_ECUDA;
+    if (make_map(&m.vt, b + w.vt, (uint64_t)B * 128, Lpad, Lpad, 64)) return MTTS_ECUDA;
+  }
+  const uint64_t rT = w.rowsT, rH = w.rowsH;
+  if (make_map(&P.x0, b + w.x0, rT, w.cinp, w.cinp, 128)) return MTTS_ECUDA;
+  if (make_map(&P.skip0, b + w.skip0, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.skip0_pair, b + w.skip0, rH, 2 * C, 2 * C, 128)) return MTTS_ECUDA;  // rows (2m, 2m+1) side by side
+  if (make_map(&P.xD0, b + w.xD0, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.skip1, b + w.skip1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xD1, b + w.xD1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xM0, b + w.xM0, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xM1, b + w.xM1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xU0s, b + w.xU0s, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xU0, b + w.xU0, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xU1s, b + w.xU1s, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&P.xF, b + w.xF, rT, C, C, 128)) return MTTS_ECUDA;
+  CUDA_TRY(cudaMemsetAsync(ws, 0, w.total, stream));
+  auto res = h->plans.emplace(key, P);
+  *out = &res.first->second;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static bool can_launch(MttsHandle* h) {
+  if (h->launch_limit >= 0 && h->launch_count >= h->launch_limit) return false;
+  ++h->launch_count;
+  return true;
+}
+
+template <int BN, int EPI>
+static int set_gemm_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN>::TOTAL));
+  return 0;
+}
+
+template <int BN, int EPI>
+static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
+                       const GemmParams& p, cudaStream_t stream) {
+  if (!can_launch(h)) return 0;
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(a0, a1, wmap, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static void segs_taps(GemmParams& p, int ntaps, const int* shifts, int cols0, int cols1) {
+  p.num_segs = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    p.seg[p.num_segs++] = GemmSeg{0, shifts[t], 0, cols0 / 64};
+    if (cols1) p.seg[p.num_segs++] = GemmSeg{1, shifts[t], 0, cols1 / 64};
+  }
+}
+static const int kTaps3[3] = {-1, 0, 1};
+static const int kTap1[1] = {0};
+
+struct LevelCtx {
+  int lv, L, Lp, rows, Lpad;
+  const float* mask;
+  const int* rowb;
+  const int* npad;
+};
+
+// One resnet + transformer stage (reference ResnetBlock1D :785-790 + BasicTransformerBlock :733-744).
+static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CUtensorMap& in0, const CUtensorMap& in1,
+                     __half* out, int t_off, int t_stride, cudaStream_t stream) {
+  const WsLayout& w = P.w;
+  const StageW& sw = h->st[s];
+  char* ws = P.ws;
+  const char* ar = h->arena;
+  const int C = h->cfg.channels;
+  const LevelMaps& lm = P.lv[lc.lv];
+  auto H = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
+  auto F = [&](size_t off) { return reinterpret_cast<const float*>(ar + off); };
+  float* part = reinterpret_cast<float*>(ws + w.part);
+  const float* te6 = reinterpret_cast<const float*>(ws + w.te6);
+
+  GemmParams base{};
+  base.M = lc.rows; base.rowb = lc.rowb; base.Lp = lc.Lp; base.mask_mul = 1; base.mask_nstep = 0;
+  base.stats_part = part; base.S = w.S; base.ldo = C; base.ldr = C;
+
+  // conv1 (k3) -> y, GroupNorm partial sums
+  {
+    GemmParams p = base;
+    segs_taps(p, 3, kTaps3, sw.src_cols[0], sw.src_cols[1]);
+    p.n_tiles = 1; p.bias = F(sw.c1_b); p.out = H(w.y);
+    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream)) return e;
+  }
+  // res_conv (1x1) -> res
+  {
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, sw.src_cols[0], sw.src_cols[1]);
+    p.n_tiles = 1; p.bias = F(sw.res_b); p.out = H(w.res);
+    if (int e = launch_gemm<256, EPI_PLAIN>(h, in0, in1, sw.m_res, p, stream)) return e;
+  }
+  const dim3 gn_grid((lc.Lp + 63) / 64, w.B);
+  // h1 = (Mish(GN(y))*m + temb)*m
+  {
+    GnParams g{};
+    g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
+    g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
+    g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
+    if (can_launch(h)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+  }
+  // conv2 (k3) -> y, partial sums
+  {
+    GemmParams p = base;
+    segs_taps(p, 3, kTaps3, C, 0);
+    p.n_tiles = 1; p.bias = F(sw.c2_b); p.out = H(w.y);
+    if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream)) return e;
+  }
+  // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
+  {
+    GnParams g{};
+    g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
+    g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
+    g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
+    if (can_launch(h)) { gn_apply_kernel<1><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+  }
+  // q | k | v^T
+  {
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, C, 0);
+    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
+    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream)) return e;
+  }
+  // attention -> o
+  if (can_launch(h)) {
+    AttnParams ap{};
+    ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
+    ap.vt = H(w.vt); ap.out = H(w.o);
+    dim3 grid((lc.L + 127) / 128, 2, w.B);
+    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(lm.q, lm.k, lm.vt, ap);
+    CUDA_TRY(cudaGetLastError());
+  }
+  // x_a = x_r + o Wo^T + b ; c = LN3(x_a)
+  {
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, 128, 0);
+    p.n_tiles = 1; p.bias = F(sw.o_b); p.resid = H(w.xr); p.out = H(w.xa);
+    p.ln_g = F(sw.ln3_g); p.ln_b = F(sw.ln3_b); p.out2 = H(w.a);
+    if (int e = launch_gemm<256, EPI_LN>(h, lm.o, lm.o, sw.m_wo, p, stream)) return e;
+  }
+  // s = SnakeBeta(c W1^T + b1)
+  {
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, C, 0);
+    p.n_tiles = 4; p.bias = F(sw.ff1_b); p.sn_a = F(sw.sn_a); p.sn_ib = F(sw.sn_ib); p.out = H(w.s); p.ldo = 4 * C;
+    if (int e = launch_gemm<256, EPI_SNAKE>(h, lm.a, lm.a, sw.m_ff1, p, stream)) return e;
+  }
+  // out = (x_a + s W2^T + b2) * m      (every consumer of a stage output masks it first)
+  {
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, 4 * C, 0);
+    p.n_tiles = 1; p.bias = F(sw.ff2_b); p.resid = H(w.xa); p.rowmask = lc.mask; p.out = out;
+    if (int e = launch_gemm<256, EPI_PLAIN>(h, lm.s, lm.s, sw.m_ff2, p, stream)) return e;
+  }
+  return 0;
+}
+
+// One estimator evaluation on the operand buffer X0 (z | mu | spks already staged, masked).
+// Writes zout = (zbase ? zbase + zscale * v : v) in (B, 80, T) fp32 and, if upd_x0, refreshes the
+// z channels of X0 with zout * mask for the next evaluation.
+static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float* zout, const float* zbase, float zscale,
+                         bool upd_x0, cudaStream_t stream) {
+  const WsLayout& w = P.w;
+  char* ws = P.ws;
+  const char* ar = h->arena;
+  const int C = h->cfg.channels;
+  auto H = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
+  auto F = [&](size_t off) { return reinterpret_cast<const float*>(ar + off); };
+  LevelCtx lT{0, w.T, w.LpT, w.rowsT, w.LpadT, reinterpret_cast<const float*>(ws + w.maskT),
+              reinterpret_cast<const int*>(ws + w.rowbT), reinterpret_cast<const int*>(ws + w.npadT)};
+  LevelCtx lH{1, w.H, w.LpH, w.rowsH, w.LpadH, reinterpret_cast<const float*>(ws + w.maskH),
+              reinterpret_cast<const int*>(ws + w.rowbH), reinterpret_cast<const int*>(ws + w.npadH)};
+  float* part = reinterpret_cast<float*>(ws + w.part);
+
+  auto level_conv = [&](const CUtensorMap& in, const CUtensorMap& wmap, size_t bias, const LevelCtx& lc, __half* out,
+                        int mode) -> int {
+    GemmParams p{};
+    p.rowb = lc.rowb; p.Lp = lc.Lp; p.ldr = C; p.bias = F(bias); p.out = out; p.rowmask = lc.mask;
+    p.mask_mul = 1; p.mask_nstep = 0; p.ldo = C; p.n_tiles = 1; p.M = lc.rows;
+    if (mode == 0) {  // k3 s1
+      segs_taps(p, 3, kTaps3, C, 0);
+    } else if (mode == 1) {  // k3 s2 on the row-pair view: x[2m-1], x[2m], x[2m+1]
+      p.num_segs = 3;
+      p.seg[0] = GemmSeg{0, -1, C, C / 64};
+      p.seg[1] = GemmSeg{0, 0, 0, C / 64};
+      p.seg[2] = GemmSeg{0, 0, C, C / 64};
+    } else {  // ConvTranspose k4 s2: M = input rows, output viewed as [rowsH, 2C], mask per output row
+      segs_taps(p, 3, kTaps3, C, 0);
+      p.n_tiles = 2; p.ldo = 2 * C; p.mask_mul = 2; p.mask_nstep = 1; p.M = lH.rows;
+    }
+    return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream);
+  };
+
+  // down 0 @T
+  if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
+  if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
+  // down 1 @T/2
+  if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
+  if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
+  // mid
+  if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
+  if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
+  // up 0 @T/2 : cat[x, skip1]
+  if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
+  {
+    LevelCtx lc = lT;  // mask of the OUTPUT rows (level T), indexed 2*r + phase
+    if (int e = level_conv(P.xU0s, h->m_up0, h->b_up0, lc, H(w.xU0), 2)) return e;
+  }
+  // up 1 @T : cat[x, skip0]
+  if (int e = run_stage(h, P, 5, lT, P.xU0, P.skip0, H(w.xU1s), t_off, t_stride, stream)) return e;
+  if (int e = level_conv(P.xU1s, h->m_up1, h->b_up1, lT, H(w.xF), 0)) return e;
+  // final block + projection + ODE update
+  {
+    GemmParams p{};
+    p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
+    segs_taps(p, 3, kTaps3, C, 0);
+    p.n_tiles = 1; p.bias = F(h->b_fin); p.out = H(w.y);
+    if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream)) return e;
+    GnParams g{};
+    g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
+    g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
+    const dim3 gn_grid((lT.Lp + 63) / 64, w.B);
+    if (can_launch(h)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+    GemmParams f{};
+    f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
+    segs_taps(f, 1, kTap1, C, 0);
+    f.n_tiles = 1; f.bias = F(h->b_proj);
+    f.zout = zout; f.zbase = zbase; f.zscale = zscale; f.x0 = upd_x0 ? H(w.x0) : nullptr; f.ldx0 = w.cinp;
+    f.T = w.T; f.n_valid = h->cfg.out_channels;
+    if (int e = launch_gemm<128, EPI_FINAL>(h, P.lv[0].h1, P.lv[0].h1, h->m_proj, f, stream)) return e;
+  }
+  return 0;
+}
+
+// masks, row maps, operand buffer, and the time-embedding table for n_t time values in ws.tvals
+static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu, const float* mask, const float* spks,
+                        int n_t, cudaStream_t stream) {
+  const WsLayout& w = P.w;
+  char* ws = P.ws;
+  const char* ar = h->arena;
+  const int C = h->cfg.channels, Cin = h->cfg.in_channels, TD = 4 * C;
+  auto Fw = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto Fa = [&](size_t off) { return reinterpret_cast<const float*>(ar + off); };
+  CUDA_TRY(cudaMemsetAsync(ws + w.vt, 0, w.vt_bytes, stream));
+  if (can_launch(h)) {
+    mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
+                                              reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
+                                              reinterpret_cast<int*>(ws + w.npadH));
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (can_launch(h)) {
+    dim3 grid((w.LpT + 31) / 32, w.B);
+    prep_x0_kernel<<<grid, 256, w.cinp * 33 * sizeof(float), stream>>>(
+        x, mu, spks, Fw(w.maskT), w.T, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (can_launch(h)) {
+    sinus_emb_kernel<<<(n_t * (Cin / 2) + 255) / 256, 256, 0, stream>>>(Fw(w.tvals), Fa(h->freqs), n_t, Cin / 2, Fw(w.te_e));
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (can_launch(h)) {
+    small_linear_kernel<<<(TD + 7) / 8, 256, 0, stream>>>(Fw(w.te_e), Fa(h->tw1), Fa(h->tb1), Fw(w.te_h1), n_t, Cin, TD, 1);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (can_launch(h)) {  // Mish applied here is the nn.Mish at the head of every ResnetBlock1D.mlp (:780)
+    small_linear_kernel<<<(TD + 7) / 8, 256, 0, stream>>>(Fw(w.te_h1), Fa(h->tw2), Fa(h->tb2), Fw(w.te_h2), n_t, TD, TD, 2);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (can_launch(h)) {
+    small_linear_kernel<<<(6 * C + 7) / 8, 256, 0, stream>>>(Fw(w.te_h2), Fa(h->mlpW), Fa(h->mlpB), Fw(w.te6), n_t, TD,
+                                                              6 * C, 0);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mtts_last_error(void) { return g_err.c_str(); }
+const char* mtts_version(void) { return "matcha_tts_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
+  if (!cfg || !out) return fail(MTTS_EINVAL, "null argument");
+  if (cfg->channels != 256 || cfg->heads != 2 || cfg->head_dim != 64 || cfg->out_channels != 80 ||
+      cfg->n_mid_blocks != 2)
+    return fail(MTTS_EINVAL, "unsupported architecture: need channels=256, heads=2, head_dim=64, out_channels=80, "
+                             "n_mid_blocks=2");
+  if (cfg->in_channels < 2 * cfg->out_channels || cfg->in_channels > 256 || (cfg->in_channels % 16) != 0)
+    return fail(MTTS_EINVAL, "unsupported in_channels: need 160 <= in_channels <= 256, multiple of 16");
+  MttsHandle* h = new MttsHandle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->cinp = (int)align_up(cfg->in_channels, 64);
+  h->nspk = cfg->in_channels - 2 * cfg->out_channels;
+  h->num_sms = 148;
+  build_tables(h);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    // on a GPU box: bind the device and opt the kernels into their dynamic shared memory sizes
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+      delete h;
+      return fail(MTTS_ECUDA, "cudaSetDevice / cudaGetDeviceProperties failed");
+    }
+    if (prop.major != 10) {
+      delete h;
+      return fail(MTTS_ECUDA, "this library contains sm_100a code only; device is not Blackwell (cc 10.x)");
+    }
+    h->num_sms = prop.multiProcessorCount;
+    int e = 0;
+    e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
+    e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV>(); e |= set_gemm_attr<128, EPI_FINAL>();
+    e |= set_gemm_attr<128, EPI_PLAIN>();
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
+    if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
+  } else {
+    cudaGetLastError();  // no GPU: tables/sizes still work (used by the CPU-side tests); compute calls will fail
+  }
+  *out = h;
+  return 0;
+}
+
+void mtts_destroy(MttsHandle* h) {
+  if (!h) return;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+  delete h;
+}
+
+int mtts_num_weights(const MttsHandle* h) { return h ? (int)h->entries.size() : 0; }
+const char* mtts_weight_name(const MttsHandle* h, int idx) {
+  if (!h || idx < 0 || idx >= (int)h->entries.size()) return nullptr;
+  return h->entries[idx].name.c_str();
+}
+int64_t mtts_weight_numel(const MttsHandle* h, int idx) {
+  if (!h || idx < 0 || idx >= (int)h->entries.size()) return -1;
+  return h->entries[idx].numel;
+}
+size_t mtts_weight_arena_bytes(const MttsHandle* h) { return h ? h->arena_bytes : 0; }
+
+int mtts_set_weight_arena(MttsHandle* h, void* dev_arena, size_t bytes, void* stream) {
+  if (!h || !dev_arena) return fail(MTTS_EINVAL, "null argument");
+  if (bytes < h->arena_bytes) return fail(MTTS_ENOMEM, "weight arena too small (see mtts_weight_arena_bytes)");
+  if ((reinterpret_cast<uintptr_t>(dev_arena) & 255) != 0) return fail(MTTS_EINVAL, "arena must be 256-byte aligned");
+  h->arena = static_cast<char*>(dev_arena);
+  CUDA_TRY(cudaMemsetAsync(dev_arena, 0, h->arena_bytes, static_cast<cudaStream_t>(stream)));
+  for (auto& e : h->entries) e.loaded = false;
+  h->plans.clear();
+  return build_weight_maps(h);
+}
+
+int mtts_load_weight(MttsHandle* h, int idx, const float* src, int64_t numel, void* stream_) {
+  if (!h || !src) return fail(MTTS_EINVAL, "null argument");
+  if (!h->arena) return fail(MTTS_ESTATE, "mtts_set_weight_arena must be called first");
+  if (idx < 0 || idx >= (int)h->entries.size()) return fail(MTTS_EINVAL, "weight index out of range");
+  WEntry& e = h->entries[idx];
+  if (numel != e.numel)
+    return fail(MTTS_EINVAL, "size mismatch for " + e.name + ": expected " + std::to_string(e.numel) + " elements, got " +
+                                 std::to_string(numel));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  for (const PackOp& o : e.ops) {
+    if (o.kind == 0) {
+      const long total = (long)o.N * o.C;
+      pack2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+          src, reinterpret_cast<__half*>(h->arena + o.dst), o.N, o.C, o.sn, o.sc, o.off, o.n_off, o.ldd, o.k_off, o.scale);
+    } else {
+      packf_kernel<<<(o.N + 255) / 256, 256, 0, stream>>>(src, reinterpret_cast<float*>(h->arena + o.dst), o.N, o.mode);
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  e.loaded = true;
+  return 0;
+}
+
+int mtts_weights_loaded(const MttsHandle* h) {
+  if (!h) return 0;
+  for (const auto& e : h->entries)
+    if (!e.loaded) return 0;
+  return 1;
+}
+
+size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T) {
+  WsLayout w;
+  if (!h || !ws_layout(h, B, T, &w)) return 0;
+  return w.total;
+}
+
+static int check_ready(MttsHandle* h) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  if (!h->arena || !h->maps_ready) return fail(MTTS_ESTATE, "weight arena not set");
+  if (!mtts_weights_loaded(h)) {
+    for (const auto& e : h->entries)
+      if (!e.loaded) return fail(MTTS_ESTATE, "weight not loaded: " + e.name);
+  }
+  return 0;
+}
+
+int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const float* mask, const float* t,
+                           const float* spks, float* out, void* workspace, size_t workspace_bytes, int B, int T,
+                           void* stream_) {
+  if (int e = check_ready(h)) return e;
+  if (!x || !mu || !mask || !t || !out || !workspace) return fail(MTTS_EINVAL, "null tensor argument");
+  if ((h->nspk > 0) != (spks != nullptr))
+    return fail(MTTS_EINVAL, "spks must be given iff in_channels > 2*out_channels");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Plan* P;
+  if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
+  h->launch_count = 0;
+  CUDA_TRY(cudaMemcpyAsync(P->ws + P->w.tvals, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream));
+  if (int e = run_prologue(h, *P, x, mu, mask, spks, B, stream)) return e;
+  return run_estimator(h, *P, /*t_off=*/0, /*t_stride=*/1, out, nullptr, 1.f, false, stream);
+}
+
+static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, const float* mask, const float* spks, int n,
+                         int solver, cudaStream_t stream) {
+  const WsLayout& w = P.w;
+  const int n_t = solver == MTTS_SOLVER_MIDPOINT ? 2 * n : n;
+  if (can_launch(h)) {
+    solver_times_kernel<<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(P.ws + w.tvals), n,
+                                                             solver == MTTS_SOLVER_MIDPOINT);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (int e = run_prologue(h, P, z, mu, mask, spks, n_t, stream)) return e;
+  const float dt = (float)(1.0 / (double)n);
+  float* zmid = reinterpret_cast<float*>(P.ws + w.zmid);
+  for (int i = 0; i < n; ++i) {
+    if (solver == MTTS_SOLVER_EULER) {
+      if (int e = run_estimator(h, P, i, 0, z, z, dt, true, stream)) return e;
+    } else {
+      if (int e = run_estimator(h, P, 2 * i, 0, zmid, z, dt * 0.5f, true, stream)) return e;
+      if (int e = run_estimator(h, P, 2 * i + 1, 0, z, z, dt, true, stream)) return e;
+    }
+  }
+  return 0;
+}
+
+int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask, const float* spks, int n, int solver,
+                     void* workspace, size_t workspace_bytes, int B, int T, int use_graph, void* stream_) {
+  if (int e = check_ready(h)) return e;
+  if (!z || !mu || !mask || !workspace) return fail(MTTS_EINVAL, "null tensor argument");
+  if ((h->nspk > 0) != (spks != nullptr))
+    return fail(MTTS_EINVAL, "spks must be given iff in_channels > 2*out_channels");
+  if (n < 1 || 2 * n > kMaxTimes) return fail(MTTS_EINVAL, "n_timesteps out of range [1, 1024]");
+  if (solver != MTTS_SOLVER_EULER && solver != MTTS_SOLVER_MIDPOINT) return fail(MTTS_EINVAL, "unknown solver");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Plan* P;
+  if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
+  h->launch_count = 0;
+  if (!use_graph || h->launch_limit >= 0) return enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
+
+  GraphKey key{z, mu, mask, spks, workspace, B, T, n, solver};
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int e = enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    if (ce != cudaSuccess) return fail(MTTS_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(MTTS_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+    if (h->graphs.size() >= 64) {  // bound the cache
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+      h->graphs.clear();
+    }
+    it = h->graphs.emplace(key, std::make_pair(exec, h->launch_count)).first;
+  }
+  h->launch_count = it->second.second;  // kernels inside the (cached) graph
+  CUDA_TRY(cudaGraphLaunch(it->second.first, stream));
+  return 0;
+}
+
+int mtts_last_launch_count(const MttsHandle* h) { return h ? h->launch_count : 0; }
+
+int mtts_debug_set_launch_limit(MttsHandle* h, int n) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  h->launch_limit = n;
+  return 0;
+}
+
+int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, const char* name) {
+  WsLayout w;
+  if (!h || !name || !ws_layout(h, B, T, &w)) return -1;
+  (void)level;
+  const std::map<std::string, size_t> m = {
+      {"maskT", w.maskT}, {"maskH", w.maskH}, {"rowbT", w.rowbT}, {"rowbH", w.rowbH}, {"npadT", w.npadT},
+      {"npadH", w.npadH}, {"tvals", w.tvals}, {"te_e", w.te_e},   {"te_h1", w.te_h1}, {"te_h2", w.te_h2},
+      {"te6", w.te6},     {"part", w.part},   {"x0", w.x0},       {"y", w.y},         {"res", w.res},
+      {"h1", w.h1},       {"xr", w.xr},       {"a", w.a},         {"xa", w.xa},       {"q", w.q},
+      {"k", w.k},         {"o", w.o},         {"vt", w.vt},       {"s", w.s},         {"skip0", w.skip0},
+      {"xD0", w.xD0},     {"skip1", w.skip1}, {"xD1", w.xD1},     {"xM0", w.xM0},     {"xM1", w.xM1},
+      {"xU0s", w.xU0s},   {"xU0", w.xU0},     {"xU1s", w.xU1s},   {"xF", w.xF},       {"zmid", w.zmid}};
+  auto it = m.find(name);
+  return it == m.end() ? -1 : (int64_t)it->second;
+}
+
+int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
+                    int ntaps, const int* shifts, void* stream_) {
+  if (!h || !A || !W || !out) return fail(MTTS_EINVAL, "null argument");
+  if (C % 64 || N % 128 || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
+  if (int e = init_encode()) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUtensorMap ma, mw;
+  GemmParams p{};
+  p.M = rows; p.bias = bias; p.out = static_cast<__half*>(out); p.ldo = N; p.mask_mul = 1;
+  segs_taps(p, ntaps, shifts, C, 0);
+  const int saved = h->launch_limit;
+  h->launch_limit = -1;
+  int e;
+  if (N % 256 == 0) {
+    if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 256)) return MTTS_ECUDA;
+    p.n_tiles = N / 256;
+    e = launch_gemm<256, EPI_PLAIN>(h, ma, ma, mw, p, stream);
+  } else {
+    if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;
+    p.n_tiles = N / 128;
+    e = launch_gemm<128, EPI_PLAIN>(h, ma, ma, mw, p, stream);
+  }
+  h->launch_limit = saved;
+  return e;
+}
+
+}  // extern "C"

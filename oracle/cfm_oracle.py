@@ -155,6 +155,13 @@ class Emu:
     conv_out: Optional[torch.dtype] = None    # raw conv output stored before GroupNorm
     attn: Optional[torch.dtype] = None        # q, k, v and the softmax probabilities
     resid: Optional[torch.dtype] = None       # transformer residual stream (resnet out, post-attention)
+    trace: Optional[dict] = None              # if a dict: named intermediates are recorded into it
+    prefix: str = ""
+
+    def tr(self, name: str, x: Tensor) -> Tensor:
+        if self.trace is not None:
+            self.trace[self.prefix + name] = x.detach().clone()
+        return x
 
     def op(self, x: Tensor) -> Tensor:
         return x if self.operand is None else x.to(self.operand).float()
@@ -199,7 +206,7 @@ def _conv(x, w, b, emu: Emu, **kw):
 def block1d(sd, pfx: str, x: Tensor, m: Tensor, cfg: DecoderCfg, emu: Emu) -> Tensor:
     """model.py:773-775 -- Mish(GroupNorm8(Conv1d k3 p1 (x*m))) * m; GN stats span ALL frames."""
     y = _conv(x * m, sd[pfx + ".block.0.weight"], sd[pfx + ".block.0.bias"], emu, padding=1)
-    y = emu.co(y)
+    y = emu.tr("y." + pfx.rsplit(".", 1)[-1], emu.co(y))
     y = F.group_norm(y, cfg.groups, sd[pfx + ".block.1.weight"], sd[pfx + ".block.1.bias"], eps=1e-5)
     return F.mish(y) * m
 
@@ -209,8 +216,10 @@ def resnet_block(sd, pfx: str, x: Tensor, m: Tensor, temb: Tensor, cfg: DecoderC
     h = block1d(sd, pfx + ".block1", x, m, cfg, emu)
     tau = F.linear(F.mish(temb), sd[pfx + ".mlp.1.weight"], sd[pfx + ".mlp.1.bias"])
     h = h + tau.unsqueeze(-1)
+    emu.tr("h1", h * m)
     h = block1d(sd, pfx + ".block2", h, m, cfg, emu)
-    return h + _conv(x * m, sd[pfx + ".res_conv.weight"], sd[pfx + ".res_conv.bias"], emu)
+    res = emu.tr("res", _conv(x * m, sd[pfx + ".res_conv.weight"], sd[pfx + ".res_conv.bias"], emu))
+    return h + res
 
 
 def attention(sd, pfx: str, a: Tensor, key_mask: Tensor, cfg: DecoderCfg, emu: Emu) -> Tensor:
@@ -225,12 +234,13 @@ def attention(sd, pfx: str, a: Tensor, key_mask: Tensor, cfg: DecoderCfg, emu: E
     q = F.linear(ao, emu.op(sd[pfx + ".to_q.weight"]))
     k = F.linear(ao, emu.op(sd[pfx + ".to_k.weight"]))
     v = F.linear(ao, emu.op(sd[pfx + ".to_v.weight"]))
+    emu.tr("q", q); emu.tr("k", k); emu.tr("v", v)
     q, k, v = (emu.at(z).reshape(B, L, H, D).permute(0, 2, 1, 3) for z in (q, k, v))
     sim = torch.matmul(q, k.transpose(-1, -2)) * (D ** -0.5)
     fill = -torch.finfo(sim.dtype).min
     sim = sim.masked_fill(key_mask.reshape(B, 1, 1, L) == 0, fill)
     p = sim.softmax(dim=-1) if emu.attn is None else _emu_softmax(sim, emu)
-    o = torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B, L, H * D)
+    o = emu.tr("o", torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B, L, H * D))
     return F.linear(emu.op(o), emu.op(sd[pfx + ".to_out.0.weight"]), sd[pfx + ".to_out.0.bias"])
 
 
@@ -246,23 +256,27 @@ def snake_ff(sd, pfx: str, c: Tensor, emu: Emu) -> Tensor:
     u = F.linear(emu.op(c), emu.op(sd[pfx + ".net.0.proj.weight"]), sd[pfx + ".net.0.proj.bias"])
     ea = torch.exp(sd[pfx + ".net.0.alpha"])
     eb = torch.exp(sd[pfx + ".net.0.beta"])
-    s = u + (1.0 / (eb + 1e-9)) * torch.sin(u * ea) ** 2
+    s = emu.tr("s", u + (1.0 / (eb + 1e-9)) * torch.sin(u * ea) ** 2)
     return F.linear(emu.op(s), emu.op(sd[pfx + ".net.2.weight"]), sd[pfx + ".net.2.bias"])
 
 
 def transformer_block(sd, pfx: str, x: Tensor, key_mask: Tensor, cfg: DecoderCfg, emu: Emu) -> Tensor:
     """model.py:733-744 -- pre-LN self-attention then pre-LN SnakeBeta FF, both residual."""
     C = cfg.channels
-    a = F.layer_norm(x, (C,), sd[pfx + ".norm1.weight"], sd[pfx + ".norm1.bias"], eps=1e-5)
-    x = emu.rs(attention(sd, pfx + ".attn1", a, key_mask, cfg, emu) + x)
-    c = F.layer_norm(x, (C,), sd[pfx + ".norm3.weight"], sd[pfx + ".norm3.bias"], eps=1e-5)
+    a = emu.tr("a", F.layer_norm(x, (C,), sd[pfx + ".norm1.weight"], sd[pfx + ".norm1.bias"], eps=1e-5))
+    x = emu.tr("xa", emu.rs(attention(sd, pfx + ".attn1", a, key_mask, cfg, emu) + x))
+    c = emu.tr("c", F.layer_norm(x, (C,), sd[pfx + ".norm3.weight"], sd[pfx + ".norm3.bias"], eps=1e-5))
     return snake_ff(sd, pfx + ".ff", c, emu) + x
 
 
 def _stage(sd, name, x, m, temb, cfg, emu):
-    x = emu.rs(resnet_block(sd, name + ".0", x, m, temb, cfg, emu))
+    emu.prefix = name + ":"
+    x = emu.tr("xr", emu.rs(resnet_block(sd, name + ".0", x, m, temb, cfg, emu)))
     x = transformer_block(sd, name + ".1.0", x.transpose(1, 2), m[:, 0, :], cfg, emu)
-    return x.transpose(1, 2)
+    x = x.transpose(1, 2)
+    emu.tr("out", x * m)          # the CUDA pipeline stores stage outputs already masked
+    emu.prefix = ""
+    return x
 
 
 # ----------------------------------------------------------------------------------------
@@ -271,7 +285,7 @@ def _stage(sd, name, x, m, temb, cfg, emu):
 def estimator_forward(sd, cfg: DecoderCfg, x: Tensor, mask: Tensor, mu: Tensor, t: Tensor,
                       spks: Optional[Tensor] = None, emu: Emu = _NOEMU) -> Tensor:
     """model.py:964-1048.  x, mu: (B,80,T); mask: (B,1,T) float; t: (B,) -> (B,80,T)."""
-    temb = time_embedding(sd, t, cfg)
+    temb = emu.tr("temb", time_embedding(sd, t, cfg))
     x = torch.cat([x, mu], dim=1)
     if spks is not None:
         x = torch.cat([x, spks.unsqueeze(-1).expand(-1, -1, x.shape[-1])], dim=1)
@@ -282,9 +296,11 @@ def estimator_forward(sd, cfg: DecoderCfg, x: Tensor, mask: Tensor, mu: Tensor, 
     skip0 = x
     x = _conv(x * m0, sd["down_blocks.0.2.conv.weight"], sd["down_blocks.0.2.conv.bias"], emu,
               stride=2, padding=1)
+    emu.tr("xD0", x * m1)
     x = _stage(sd, "down_blocks.1", x, m1, temb, cfg, emu)
     skip1 = x
     x = _conv(x * m1, sd["down_blocks.1.2.weight"], sd["down_blocks.1.2.bias"], emu, padding=1)
+    emu.tr("xD1", x * m1)
 
     for i in range(cfg.n_mid):
         x = _stage(sd, f"mid_blocks.{i}", x, m1, temb, cfg, emu)
@@ -294,10 +310,12 @@ def estimator_forward(sd, cfg: DecoderCfg, x: Tensor, mask: Tensor, mu: Tensor, 
                            sd["up_blocks.0.2.conv.bias"], stride=2, padding=1)
     if x.shape[-1] != skip0.shape[-1]:                       # odd T: nearest-resize == crop
         x = F.interpolate(x, size=skip0.shape[-1], mode="nearest")
+    emu.tr("xU0", x * m0)
     x = _stage(sd, "up_blocks.1", torch.cat([x, skip0], dim=1), m0, temb, cfg, emu)
     x = _conv(x * m0, sd["up_blocks.1.2.weight"], sd["up_blocks.1.2.bias"], emu, padding=1)
+    emu.tr("xF", x * m0)
 
-    x = block1d(sd, "final_block", x, m0, cfg, emu)
+    x = emu.tr("hF", block1d(sd, "final_block", x, m0, cfg, emu))
     out = _conv(x * m0, sd["final_proj.weight"], sd["final_proj.bias"], emu)
     return out * mask
 

@@ -23,17 +23,12 @@ sys.dont_write_bytecode = True
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 sys.path.insert(0, "/root/reference")
 
 import model as ref                                   # noqa: E402  (the reference itself)
 from oracle import cfm_oracle as O                    # noqa: E402
-
-
-def sd_checksum(sd):
-    acc = 0.0
-    for i, k in enumerate(sorted(sd)):
-        acc += float(sd[k].double().sum()) * (1 + (i % 7)) + float(sd[k].double().abs().sum())
-    return acc
+from make_golden_cases import CASES, sd_checksum      # noqa: E402
 
 
 def ref_decoder(cfg, sd):
@@ -69,14 +64,6 @@ def check(name, a, b, tol=2e-5):
     assert err <= tol, (name, err)
 
 
-CASES = [
-    # name, in_channels, B, T, lengths, n_timesteps, solver, seed
-    ("lj_full", 160, 2, 32, [32, 32], 3, "euler", 11),
-    ("lj_ragged", 160, 3, 48, [48, 31, 17], 2, "euler", 12),
-    ("vctk_ragged", 224, 2, 24, [24, 10], 2, "euler", 13),
-    ("lj_midpoint", 160, 1, 16, [16], 2, "midpoint", 14),
-    ("lj_long", 160, 1, 200, [200], 1, "euler", 15),
-]
 
 
 def main():

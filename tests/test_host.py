@@ -1,0 +1,162 @@
+"""Host-side logic and the C-ABI boundary on CPU: the library loads and exports every symbol
+include/mtts.h declares, its weight table equals the reference state-dict layout, and the
+drop-in modules keep the reference's constructor / error behaviour.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import types
+
+import pytest
+import torch
+
+from oracle import cfm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = os.path.exists("/root/reference/model.py")
+
+
+def _ref():
+    import sys
+    sys.dont_write_bytecode = True
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import model as ref
+    return ref
+
+
+def test_header_symbols_exported(libmtts):
+    from matcha_tts_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mtts.h")).read()
+    declared = set(re.findall(r"\b(mtts_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no prototypes found in mtts.h"
+    for name in declared:
+        assert hasattr(libmtts, name), f"libmtts.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and mtts.h disagree"
+    assert b"sm_100a" in libmtts.mtts_version()
+
+
+@pytest.mark.parametrize("cin", [160, 224])
+def test_weight_table_matches_state_dict(libmtts, cin):
+    from matcha_tts_b200 import _lib
+    from matcha_tts_b200.model import estimator_param_spec
+    cfg = _lib.MttsConfig(cin, 80, 256, 2, 64, 2)
+    h = C.c_void_p()
+    _lib.check(libmtts.mtts_create(C.byref(cfg), 0, C.byref(h)))
+    n = libmtts.mtts_num_weights(h)
+    table = [(libmtts.mtts_weight_name(h, i).decode(), libmtts.mtts_weight_numel(h, i)) for i in range(n)]
+    spec = estimator_param_spec(cin, 80, 256, 2, 64, 2)
+    assert spec == O.state_dict_spec(O.DecoderCfg(in_channels=cin))      # package mirror == oracle == App. B
+    want = [("@time_freqs", cin // 2)] + [(k, int(torch.Size(s).numel())) for k, s in spec]
+    assert table == want
+    assert libmtts.mtts_weight_arena_bytes(h) > 2 * sum(x[1] for x in want if "block.0.weight" in x[0])
+    # workspace sizing: valid and invalid shapes
+    assert libmtts.mtts_workspace_bytes(h, 64, 344) > 0
+    assert libmtts.mtts_workspace_bytes(h, 1, 2) > 0
+    assert libmtts.mtts_workspace_bytes(h, 4, 33) == 0          # odd T
+    assert libmtts.mtts_workspace_bytes(h, 0, 32) == 0
+    assert libmtts.mtts_debug_buffer_offset(h, 2, 32, 0, b"skip0") > 0
+    assert libmtts.mtts_debug_buffer_offset(h, 2, 32, 0, b"nope") == -1
+    # call-order errors are reported, not ignored
+    assert libmtts.mtts_load_weight(h, 0, C.c_void_p(16), cin // 2, None) == -3
+    assert b"arena" in libmtts.mtts_last_error()
+    libmtts.mtts_destroy(h)
+
+
+def test_unsupported_config_is_an_error(libmtts):
+    from matcha_tts_b200 import _lib
+    h = C.c_void_p()
+    bad = _lib.MttsConfig(160, 80, 512, 2, 64, 2)
+    assert libmtts.mtts_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert b"unsupported" in libmtts.mtts_last_error()
+    with pytest.raises(_lib.MttsError):
+        _lib.check(-1)
+
+
+def test_decoder_state_dict_layout():
+    from matcha_tts_b200 import Decoder
+    dec = Decoder(in_channels=160, out_channels=80, channels=(256, 256), dropout=0.05, attention_head_dim=64,
+                  n_blocks=1, num_mid_blocks=2, num_heads=2, act_fn="snakebeta")
+    sd = dec.state_dict()
+    spec = O.state_dict_spec(O.DecoderCfg())
+    assert sorted(sd.keys()) == sorted(k for k, _ in spec)
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in spec)
+    assert sum(v.numel() for v in sd.values()) == 11_008_848
+    dec.load_state_dict(O.make_state_dict(O.DecoderCfg(), 0), strict=True)         # reference-layout weights load
+    with pytest.raises(RuntimeError):                                              # no CPU path
+        dec(torch.zeros(1, 80, 8), torch.ones(1, 1, 8), torch.zeros(1, 80, 8), torch.zeros(1))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_decoder_state_dict_equals_reference():
+    from matcha_tts_b200 import Decoder
+    ref = _ref()
+    for cin in (160, 224):
+        kw = dict(in_channels=cin, out_channels=80, channels=(256, 256), dropout=0.05, attention_head_dim=64,
+                  n_blocks=1, num_mid_blocks=2, num_heads=2, act_fn="snakebeta")
+        a, b = Decoder(**kw).state_dict(), ref.Decoder(**kw).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+        Decoder(**kw).load_state_dict(b, strict=True)
+
+
+def test_cfm_constructor_contract():
+    from matcha_tts_b200 import CFM, Decoder
+    with pytest.raises(ValueError):
+        CFM(80, {"solver": "euler"}, estimator=None)                # model.py:1131-1132
+    dec = Decoder(160, 80, num_heads=2)
+    cfm = CFM(80, {"solver": "rk4"}, estimator=dec)
+    with pytest.raises(NotImplementedError):                         # model.py:1107
+        cfm.solve_from(torch.zeros(1, 80, 8), torch.zeros(1, 80, 8), torch.ones(1, 1, 8), 2)
+    assert CFM(80, {}, estimator=dec).solver == "euler" and CFM(80, {}, estimator=dec).sigma_min == 1e-4
+    with pytest.raises(NotImplementedError):
+        Decoder(160, 80, channels=(256, 512))
+
+
+def test_host_helpers():
+    from matcha_tts_b200 import denormalize, fix_len_compatibility, generate_path, sequence_mask
+    assert fix_len_compatibility(343) == 344 and fix_len_compatibility(1) == 4
+    lens = torch.tensor([3, 1])
+    assert sequence_mask(lens, 4).tolist() == [[True, True, True, False], [True, False, False, False]]
+    dur = torch.tensor([[2.0, 1.0, 0.0], [1.0, 3.0, 0.0]])
+    mask = torch.ones(2, 3, 4)
+    p = generate_path(dur, mask)
+    assert p[0].tolist() == [[1, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]]
+    assert p[1].tolist() == [[1, 0, 0, 0], [0, 1, 1, 1], [0, 0, 0, 0]]
+    x = torch.ones(1, 2, 3)
+    assert torch.allclose(denormalize(x, -5.5, 2.0), torch.full((1, 2, 3), -3.5))
+    assert torch.allclose(denormalize(x, torch.tensor(1.0), torch.tensor(3.0)), torch.full((1, 2, 3), 4.0))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_host_helpers_equal_reference():
+    from matcha_tts_b200 import fix_len_compatibility, generate_path, sequence_mask
+    ref = _ref()
+    g = torch.Generator().manual_seed(0)
+    for _ in range(5):
+        b, tx = 3, 7
+        dur = torch.randint(0, 5, (b, tx), generator=g).float()
+        ty = int(dur.sum(1).max()) + 2
+        ylen = dur.sum(1).long()
+        xm = torch.ones(b, tx)
+        ym = ref.sequence_mask(ylen, ty).float()
+        am = xm.unsqueeze(-1) * ym.unsqueeze(1)
+        assert torch.equal(generate_path(dur, am), ref.generate_path(dur, am))
+        assert torch.equal(sequence_mask(ylen, ty), ref.sequence_mask(ylen, ty))
+    for n in (1, 4, 5, 343, 344):
+        assert fix_len_compatibility(n) == ref.fix_len_compatibility(torch.tensor(n))
+
+
+def test_matcha_facade_signature():
+    import inspect
+    from matcha_tts_b200 import MatchaTTS
+    sig = inspect.signature(MatchaTTS.synthesize)
+    assert list(sig.parameters) == ["self", "x", "x_lengths", "n_timesteps", "temperature", "spks", "length_scale"]
+    assert MatchaTTS.synthesise is MatchaTTS.synthesize
+    enc = types.SimpleNamespace(n_feats=80)
+    dp = types.SimpleNamespace(channels=(256, 256), dropout=0.05, attention_head_dim=64, n_blocks=1,
+                               num_mid_blocks=2, num_heads=2, act_fn="snakebeta")
+    m = MatchaTTS(178, 1, 64, enc, dp, {"solver": "euler", "sigma_min": 1e-4})
+    keys = list(m.state_dict().keys())
+    assert keys[0] == "mel_mean" and keys[1] == "mel_std" and keys[2].startswith("decoder.estimator.time_mlp")
+    with pytest.raises(RuntimeError):
+        m.synthesize(torch.zeros(1, 4, dtype=torch.long), torch.tensor([4]), 2)
