@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- mel-frames/sec of the CFM decoder Euler solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" is one full n_timesteps=10 Euler solve of one batch (BASELINE configs[1]: LJSpeech-shape
+decoder, B=64 utterances x T_mel=344 frames, random-init weights, synthetic mu / noise).
+  value : whole-job mel-frames/s with inputs resident in HBM (CUDA-graph replay of the solve),
+          timed per step with CUDA events, L2 flushed between steps, max over ranks.
+  e2e   : the same metric through the public API CFM.forward(mu, mask, n_timesteps, temperature)
+          with mu/mask in pinned HOST memory and the mel read back to the host every step.
+  roofline : tcgen05 GEMM kernel (all convs + linears): algorithmic FLOPs / CUDA-event time of its
+          launches inside one solve, against the measured sustained bf16 peak.
+  cpu_baseline : the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1).
+`--impl reference` times only that CPU port (bounded sample of the same workload) and prints the
+same JSON shape with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mel-frames/sec for CFM decoder sampling (10 Euler steps)"
+UNIT = "mel-frames/s"
+GEMM_FLOP_PER_FRAME_STEP = 10_985_472       # SURVEY.md App. C (conv + linear GEMMs, Cin=160)
+ATTN_FLOP_PER_FRAME_STEP_PER_T = 1536       # + 1536*T for attention
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1362.7), d.get("hbm_gbs", 6535.4), "measured"
+    return 1400.0, 6650.0, "fallback"     # B200_PROFILING.md fallback (sustained ~1.4 PF, 6.65 TB/s)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle) -- used for cpu_baseline and for --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(B, T, n_timesteps, steps, warmup, budget_s):
+    import torch
+    from oracle import cfm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cfg = O.DecoderCfg()
+    sd = O.make_state_dict(cfg, 0)
+    # size the sample (rows of the B x T batch) so that (steps + warmup) solves fit the budget
+    mu, mask, z0, _ = O.make_inputs(cfg, 1, T, None, seed=1)
+    with torch.inference_mode():
+        O.euler_solve(sd, cfg, z0, mu, mask, 1)                       # page in / thread pool start
+        t0 = time.perf_counter()
+        O.euler_solve(sd, cfg, z0, mu, mask, n_timesteps)
+        t_row = time.perf_counter() - t0
+    rows = int(max(1, min(8, B, budget_s / max(1, steps + warmup) / t_row)))
+    mu, mask, z0, _ = O.make_inputs(cfg, rows, T, None, seed=1)
+    times = []
+    with torch.inference_mode():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.euler_solve(sd, cfg, z0, mu, mask, n_timesteps)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": rows * T / mean, "ms_per_step": mean * 1e3, "cores": cores, "rows": rows,
+            "sample": f"{rows} of {B} rows x T={T}, {n_timesteps} Euler steps, fp32 torch-CPU, "
+                      f"{steps} timed solves after {warmup} warm-up (mean)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.batch, args.frames, args.n_timesteps, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, extra={"device": "host CPU", "note": "oracle port of the reference PyTorch "
+                                               "path (reference is pure Python/PyTorch; no compiled artefact)"}),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, extra=None):
+    c = {"workload": "BASELINE configs[1]: Matcha-TTS LJSpeech-shape CFM decoder (11.0 M params, random init), "
+                     f"batch {args.batch} x T_mel={args.frames}, n_timesteps={args.n_timesteps}, "
+                     + ("ragged lengths U{300..T}" if args.ragged else "all rows full length (mask all ones)"),
+         "batch": args.batch, "t_mel": args.frames, "n_timesteps": args.n_timesteps,
+         "frames_per_step": args.batch * args.frames, "parallelism": f"dp{args.gpus} (utterance-sharded, no hot-path collective)",
+         "l2": "flushed between timed steps (256 MiB write)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from matcha_tts_b200 import CFM, Decoder, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, n = args.batch, args.frames, args.n_timesteps
+
+    torch.manual_seed(0)
+    dec = Decoder(in_channels=160, out_channels=80, channels=(256, 256), dropout=0.05, attention_head_dim=64,
+                  n_blocks=1, num_mid_blocks=2, num_heads=2, act_fn="snakebeta").to(dev)
+    cfm = CFM(80, {"solver": "euler", "sigma_min": 1e-4}, estimator=dec)
+    g = torch.Generator().manual_seed(1 + rank)
+    mu_h = torch.randn(B, 80, T, generator=g).pin_memory()
+    if args.ragged:
+        lengths = torch.randint(300, T + 1, (B,), generator=g)
+        lengths[0] = T
+    else:
+        lengths = torch.full((B,), T)
+    mask_h = (torch.arange(T)[None, :] < lengths[:, None]).unsqueeze(1).float().pin_memory()
+    z0 = (torch.randn(B, 80, T, generator=g) * 0.667).to(dev)
+    mu, mask = mu_h.to(dev), mask_h.to(dev)
+    eng = dec._engine(dev)
+    stream = torch.cuda.Stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    z = torch.empty_like(z0)
+    gathered = torch.empty(world * B, 80, T, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        z.copy_(z0, non_blocking=True)
+        _lib.check(eng.lib.mtts_euler_solve(eng.h, z.data_ptr(), mu.data_ptr(), mask.data_ptr(), None, n, 0,
+                                            eng.workspace(B, T)[1], eng.workspace(B, T)[2], B, T, 1, stream.cuda_stream))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, z)          # final mel gather (NCCL over NVLink)
+
+    # ---- device-resident throughput ----
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        launches_per_step = eng.launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with ClockSampler(local) as clocks:
+            barrier()
+            for a, b in evs:
+                flush.fill_(1)                                  # evict L2 between timed steps
+                a.record(stream)
+                step_device()
+                b.record(stream)
+            barrier()
+        ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(ms)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    frames = world * B * T * args.steps
+    value = frames / (total_ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host inputs -> CFM.forward -> host mel ----
+    out_h = torch.empty(B, 80, T).pin_memory()
+    def step_e2e():
+        mu_d = mu_h.to(dev, non_blocking=True)
+        mask_d = mask_h.to(dev, non_blocking=True)
+        mel = cfm(mu_d, mask_d, n, temperature=0.667)
+        out_h.copy_(mel, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = frames / e2e_s
+
+    # ---- per-kernel timing of one solve (CUDA events around every launch) for the roofline ----
+    roof = None
+    kinds = {}
+    with torch.cuda.stream(stream):
+        z.copy_(z0)
+        torch.cuda.synchronize(dev)
+        _lib.check(eng.lib.mtts_debug_profile_begin(eng.h, stream.cuda_stream))
+        _lib.check(eng.lib.mtts_euler_solve(eng.h, z.data_ptr(), mu.data_ptr(), mask.data_ptr(), None, n, 0,
+                                            eng.workspace(B, T)[1], eng.workspace(B, T)[2], B, T, 0, stream.cuda_stream))
+        cap = 8192
+        msb, kb, fb = (C.c_float * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
+        cnt = eng.lib.mtts_debug_profile_end(eng.h, cap, msb, kb, fb)
+    if cnt > 0:
+        names = {0: "gemm_tc", 1: "attention", 2: "gn_apply", 3: "other"}
+        for i in range(min(cnt, cap)):
+            k = kinds.setdefault(names[kb[i]], {"launches": 0, "ms": 0.0, "flop": 0.0})
+            k["launches"] += 1
+            k["ms"] += msb[i]
+            k["flop"] += fb[i]
+        peak_tf, _, which = measured_peaks()
+        gm = kinds["gemm_tc"]
+        achieved = gm["flop"] / (gm["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: all convs + linears)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": f"{which} sustained bf16 (MEASURED_PEAKS.json); fp16 runs at the same tcgen05 rate",
+                "traffic": None,
+                "avg_launch_us": gm["ms"] * 1e3 / gm["launches"], "launches_per_solve": gm["launches"],
+                "algorithmic_flop_per_solve": gm["flop"],
+                "share_of_solve": {k: round(v["ms"] / sum(x["ms"] for x in kinds.values()), 4) for k, v in kinds.items()},
+                "ms_per_solve_by_kernel": {k: round(v["ms"], 4) for k, v in kinds.items()}}
+
+    if rank == 0:
+        flop_step = B * T * n * (GEMM_FLOP_PER_FRAME_STEP + ATTN_FLOP_PER_FRAME_STEP_PER_T * T)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(B, T, n, steps=3, warmup=1, budget_s=25.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": workload_config(args, extra={
+                "operands": "fp16 tensors, fp32 accumulate (bf16 operands miss the 1e-3 rel-L2 parity bar; same tensor rate)",
+                "model_tflops_per_gpu": flop_step / (total_ms / args.steps * 1e-3) / 1e12,
+                "ms_min": min(ms), "ms_max": max(ms)}),
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": mu_h.numel() * 4 + mask_h.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "CFM.forward(mu, mask, n_timesteps, temperature) with pinned-host mu/mask and mel read back"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=344)
+    ap.add_argument("--n-timesteps", type=int, default=10)
+    ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,17 @@ int mtts_euler_solve(MttsHandle* h, float* z_inout, const float* mu, const float
 /* Number of kernels enqueued by the last estimator_forward / euler_solve call on this handle. */
 int mtts_last_launch_count(const MttsHandle* h);
 
+/* Per-launch device timing for bench.py's roofline: between begin and end every kernel the library
+ * launches on `stream` is bracketed by a CUDA-event pair (graph capture is bypassed meanwhile).
+ * end() synchronises on the last event and returns the number of launches recorded, filling up to
+ * max_entries of: milliseconds, kind (MTTS_KIND_*), algorithmic FLOPs of the launch. */
+#define MTTS_KIND_GEMM 0   /* tcgen05 implicit-GEMM (convs + linears) */
+#define MTTS_KIND_ATTN 1   /* attention */
+#define MTTS_KIND_NORM 2   /* GroupNorm-apply / Mish / LayerNorm pass */
+#define MTTS_KIND_OTHER 3  /* masks, operand staging, time embedding */
+int mtts_debug_profile_begin(MttsHandle* h, void* stream);
+int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind, double* flops);
+
 /* ---- introspection used by the parity tests -------------------------------------------------- */
 /* Stop the estimator after `n` kernel launches (n < 0: run everything). */
 int mtts_debug_set_launch_limit(MttsHandle* h, int n);

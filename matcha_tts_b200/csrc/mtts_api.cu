@@ -141,6 +141,12 @@ struct MttsHandle {
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
   int launch_count = 0, launch_limit = -1;
+  // optional per-launch device timing (CUDA events on the launching stream)
+  bool profiling = false;
+  cudaStream_t prof_stream = nullptr;
+  std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
+  std::vector<int> prof_kind;            // MTTS_KIND_*
+  std::vector<double> prof_flops;        // algorithmic FLOPs of the launch
 };
 
 static const char* kStageNames[6] = {"down_blocks.0", "down_blocks.1", "mid_blocks.0",
@@ -372,10 +378,26 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static bool can_launch(MttsHandle* h) {
+static void prof_mark(MttsHandle* h) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, h->prof_stream);
+  h->prof_events.push_back(e);
+}
+// Every kernel launch goes through can_launch() ... launched(): launch counting, the debug launch
+// limit, and (when enabled) a CUDA-event pair around the launch.
+static bool can_launch(MttsHandle* h, int kind = MTTS_KIND_OTHER, double flops = 0.0) {
   if (h->launch_limit >= 0 && h->launch_count >= h->launch_limit) return false;
   ++h->launch_count;
+  if (h->profiling) {
+    h->prof_kind.push_back(kind);
+    h->prof_flops.push_back(flops);
+    prof_mark(h);
+  }
   return true;
+}
+static void launched(MttsHandle* h) {
+  if (h->profiling) prof_mark(h);
 }
 
 template <int BN, int EPI>
@@ -387,12 +409,13 @@ static int set_gemm_attr() {
 
 template <int BN, int EPI>
 static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
-                       const GemmParams& p, cudaStream_t stream) {
-  if (!can_launch(h)) return 0;
+                       const GemmParams& p, cudaStream_t stream, double aflops = 0.0) {
+  if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(a0, a1, wmap, p);
   CUDA_TRY(cudaGetLastError());
+  launched(h);
   return 0;
 }
 
@@ -427,6 +450,8 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
   float* part = reinterpret_cast<float*>(ws + w.part);
   const float* te6 = reinterpret_cast<const float*>(ws + w.te6);
 
+  const double fr = 2.0 * w.B * (double)lc.L;   // algorithmic FLOPs = fr * N * K (valid rows, unpadded K/N)
+  const int ci_real = (s == 0) ? h->cfg.in_channels : sw.src_cols[0] + sw.src_cols[1];
   GemmParams base{};
   base.M = lc.rows; base.rowb = lc.rowb; base.Lp = lc.Lp; base.mask_mul = 1; base.mask_nstep = 0;
   base.stats_part = part; base.S = w.S; base.ldo = C; base.ldr = C;
@@ -436,14 +461,14 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, sw.src_cols[0], sw.src_cols[1]);
     p.n_tiles = 1; p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 3 * ci_real)) return e;
   }
   // res_conv (1x1) -> res
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, sw.src_cols[0], sw.src_cols[1]);
     p.n_tiles = 1; p.bias = F(sw.res_b); p.out = H(w.res);
-    if (int e = launch_gemm<256, EPI_PLAIN>(h, in0, in1, sw.m_res, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_PLAIN>(h, in0, in1, sw.m_res, p, stream, fr * C * ci_real)) return e;
   }
   const dim3 gn_grid((lc.Lp + 63) / 64, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
@@ -452,14 +477,14 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
     p.n_tiles = 1; p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
   }
   // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
   {
@@ -467,23 +492,24 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
     g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-    if (can_launch(h)) { gn_apply_kernel<1><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<1><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
   }
   // q | k | v^T
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
     p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
-    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream)) return e;
+    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
   }
   // attention -> o
-  if (can_launch(h)) {
+  if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
     AttnParams ap{};
     ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
     ap.vt = H(w.vt); ap.out = H(w.o);
     dim3 grid((lc.L + 127) / 128, 2, w.B);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(lm.q, lm.k, lm.vt, ap);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   // x_a = x_r + o Wo^T + b ; c = LN3(x_a)
   {
@@ -491,21 +517,21 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     segs_taps(p, 1, kTap1, 128, 0);
     p.n_tiles = 1; p.bias = F(sw.o_b); p.resid = H(w.xr); p.out = H(w.xa);
     p.ln_g = F(sw.ln3_g); p.ln_b = F(sw.ln3_b); p.out2 = H(w.a);
-    if (int e = launch_gemm<256, EPI_LN>(h, lm.o, lm.o, sw.m_wo, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_LN>(h, lm.o, lm.o, sw.m_wo, p, stream, fr * C * 128)) return e;
   }
   // s = SnakeBeta(c W1^T + b1)
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
     p.n_tiles = 4; p.bias = F(sw.ff1_b); p.sn_a = F(sw.sn_a); p.sn_ib = F(sw.sn_ib); p.out = H(w.s); p.ldo = 4 * C;
-    if (int e = launch_gemm<256, EPI_SNAKE>(h, lm.a, lm.a, sw.m_ff1, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_SNAKE>(h, lm.a, lm.a, sw.m_ff1, p, stream, fr * 4 * C * C)) return e;
   }
   // out = (x_a + s W2^T + b2) * m      (every consumer of a stage output masks it first)
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, 4 * C, 0);
     p.n_tiles = 1; p.bias = F(sw.ff2_b); p.resid = H(w.xa); p.rowmask = lc.mask; p.out = out;
-    if (int e = launch_gemm<256, EPI_PLAIN>(h, lm.s, lm.s, sw.m_ff2, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_PLAIN>(h, lm.s, lm.s, sw.m_ff2, p, stream, fr * C * 4 * C)) return e;
   }
   return 0;
 }
@@ -543,7 +569,9 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
       segs_taps(p, 3, kTaps3, C, 0);
       p.n_tiles = 2; p.ldo = 2 * C; p.mask_mul = 2; p.mask_nstep = 1; p.M = lH.rows;
     }
-    return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream);
+    // k3 convs: out rows * 256 * 768; ConvTranspose: B*H input rows * 512 outputs * 512 (two 2-tap phases)
+    const double af = (mode == 2) ? 2.0 * w.B * (double)w.H * 512 * 512 : 2.0 * w.B * (double)lc.L * C * 3 * C;
+    return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream, af);
   };
 
   // down 0 @T
@@ -570,19 +598,19 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
     p.n_tiles = 1; p.bias = F(h->b_fin); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream)) return e;
+    if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e;
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
     const dim3 gn_grid((lT.Lp + 63) / 64, w.B);
-    if (can_launch(h)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); }
+    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
     f.n_tiles = 1; f.bias = F(h->b_proj);
     f.zout = zout; f.zbase = zbase; f.zscale = zscale; f.x0 = upd_x0 ? H(w.x0) : nullptr; f.ldx0 = w.cinp;
     f.T = w.T; f.n_valid = h->cfg.out_channels;
-    if (int e = launch_gemm<128, EPI_FINAL>(h, P.lv[0].h1, P.lv[0].h1, h->m_proj, f, stream)) return e;
+    if (int e = launch_gemm<128, EPI_FINAL>(h, P.lv[0].h1, P.lv[0].h1, h->m_proj, f, stream, 2.0 * w.B * (double)w.T * h->cfg.out_channels * C)) return e;
   }
   return 0;
 }
@@ -602,29 +630,35 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
                                               reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
                                               reinterpret_cast<int*>(ws + w.npadH));
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (can_launch(h)) {
     dim3 grid((w.LpT + 31) / 32, w.B);
     prep_x0_kernel<<<grid, 256, w.cinp * 33 * sizeof(float), stream>>>(
         x, mu, spks, Fw(w.maskT), w.T, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (can_launch(h)) {
     sinus_emb_kernel<<<(n_t * (Cin / 2) + 255) / 256, 256, 0, stream>>>(Fw(w.tvals), Fa(h->freqs), n_t, Cin / 2, Fw(w.te_e));
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (can_launch(h)) {
     small_linear_kernel<<<(TD + 7) / 8, 256, 0, stream>>>(Fw(w.te_e), Fa(h->tw1), Fa(h->tb1), Fw(w.te_h1), n_t, Cin, TD, 1);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (can_launch(h)) {  // Mish applied here is the nn.Mish at the head of every ResnetBlock1D.mlp (:780)
     small_linear_kernel<<<(TD + 7) / 8, 256, 0, stream>>>(Fw(w.te_h1), Fa(h->tw2), Fa(h->tb2), Fw(w.te_h2), n_t, TD, TD, 2);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (can_launch(h)) {
     small_linear_kernel<<<(6 * C + 7) / 8, 256, 0, stream>>>(Fw(w.te_h2), Fa(h->mlpW), Fa(h->mlpB), Fw(w.te6), n_t, TD,
                                                               6 * C, 0);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   return 0;
 }
@@ -776,6 +810,7 @@ static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, cons
     solver_times_kernel<<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(P.ws + w.tvals), n,
                                                              solver == MTTS_SOLVER_MIDPOINT);
     CUDA_TRY(cudaGetLastError());
+    launched(h);
   }
   if (int e = run_prologue(h, P, z, mu, mask, spks, n_t, stream)) return e;
   const float dt = (float)(1.0 / (double)n);
@@ -803,7 +838,7 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
   Plan* P;
   if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
   h->launch_count = 0;
-  if (!use_graph || h->launch_limit >= 0) return enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
+  if (!use_graph || h->launch_limit >= 0 || h->profiling) return enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
 
   GraphKey key{z, mu, mask, spks, workspace, B, T, n, solver};
   auto it = h->graphs.find(key);
@@ -830,6 +865,32 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
 }
 
 int mtts_last_launch_count(const MttsHandle* h) { return h ? h->launch_count : 0; }
+
+int mtts_debug_profile_begin(MttsHandle* h, void* stream) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear(); h->prof_kind.clear(); h->prof_flops.clear();
+  h->prof_stream = static_cast<cudaStream_t>(stream);
+  h->profiling = true;
+  return 0;
+}
+
+int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind, double* flops) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  h->profiling = false;
+  if (!h->prof_events.empty()) CUDA_TRY(cudaEventSynchronize(h->prof_events.back()));
+  const int n = (int)h->prof_kind.size();
+  for (int i = 0; i < n && i < max_entries; ++i) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+    if (ms) ms[i] = t;
+    if (kind) kind[i] = h->prof_kind[i];
+    if (flops) flops[i] = h->prof_flops[i];
+  }
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear(); h->prof_kind.clear(); h->prof_flops.clear();
+  return n;
+}
 
 int mtts_debug_set_launch_limit(MttsHandle* h, int n) {
   if (!h) return fail(MTTS_EINVAL, "null handle");

@@ -1,0 +1,264 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+vectors of the reference.  Floating-point path: tolerances are the ones BASELINE.json states for
+the 10-step mel (max-abs 2e-2, relative L2 1e-3 over valid frames); single estimator calls and
+unit GEMMs use the operand-rounding bounds written next to each check."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import gpu_util as U  # noqa: E402
+from make_golden_cases import CASES  # noqa: E402
+from oracle import cfm_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+EST_REL = 3e-3     # one estimator call, fp16 operands through ~60 GEMMs (the 10-step bar is on z)
+
+
+@pytest.fixture(scope="module")
+def lj():
+    return U.make_decoder(160)
+
+
+@pytest.fixture(scope="module")
+def vctk():
+    return U.make_decoder(224)
+
+
+def _d(x):
+    return None if x is None else x.cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# unit: the tcgen05 implicit-GEMM kernel vs fp32 matmul of the same fp16 operands
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,Cc,N,shifts", [
+    (1, 64, 128, [0]), (127, 64, 256, [0]), (128, 192, 256, [-1, 0, 1]), (129, 256, 256, [-1, 0, 1]),
+    (22144, 256, 256, [-1, 0, 1]), (11072, 512, 256, [0]), (5000, 256, 1024, [0]), (3000, 1024, 256, [0]),
+    (4097, 128, 384, [0]), (777, 256, 512, [-1, 0, 1]),
+])
+def test_gemm_tc(lj, rows, Cc, N, shifts):
+    dec, _, _ = lj
+    eng = dec._engine(torch.device("cuda", 0))
+    g = torch.Generator().manual_seed(rows + N)
+    A = torch.randn(rows, Cc, generator=g).half().cuda()
+    W = (torch.randn(N, len(shifts) * Cc, generator=g) / (len(shifts) * Cc) ** 0.5).half().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = bias[None, :].repeat(rows, 1)
+    Af = A.float()
+    for i, s in enumerate(shifts):
+        sh = torch.zeros_like(Af)
+        if s == 0:
+            sh = Af
+        elif s > 0:
+            sh[:-s] = Af[s:]
+        else:
+            sh[-s:] = Af[:s]
+        ref += sh @ W[:, i * Cc:(i + 1) * Cc].float().T
+    out = torch.full((rows, N), float("nan"), dtype=torch.float16, device="cuda")
+    sh = (C.c_int * len(shifts))(*shifts)
+    rc = eng.lib.mtts_debug_gemm(eng.h, A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), rows, Cc, N,
+                                 len(shifts), sh, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    # fp32 accumulate of exact fp16 products; the only rounding is the fp16 store: |err| <= 2^-11 |x|
+    assert torch.isfinite(out).all()
+    assert float((out.float() - ref).abs().max()) <= 2.0 ** -10 * float(ref.abs().max()) + 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the reference (tests/golden/cfm_golden.npz)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_against_reference_golden(case, golden, lj, vctk):
+    name, cin, B, T, lengths, n, solver, seed = case
+    dec, cfg, sd = lj if cin == 160 else vctk
+    mu, mask, z0, spks = O.make_inputs(cfg, B, T, lengths, seed=seed)
+    t = torch.linspace(0.05, 0.9, B)
+    est = dec(_d(z0), _d(mask), _d(mu), _d(t), _d(spks)).cpu()
+    ref = torch.from_numpy(golden[name + ".est"])
+    ma, rl = O.parity_errors(est, ref, mask)
+    assert ma <= O.TOL_MAX_ABS and rl <= EST_REL, (ma, rl)
+    assert float((est * (1 - mask)).abs().max()) == 0.0                      # exactly 0 at padded frames
+    z = dec.solve(_d(z0), _d(mu), _d(mask), n, _d(spks), solver, use_graph=False).cpu()
+    zr = torch.from_numpy(golden[name + ".z"])
+    ma, rl = O.parity_errors(z, zr, mask)
+    assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+    assert torch.equal(z * (1 - mask), z0 * (1 - mask))                       # padded frames keep z0 bit-exactly
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs at reduced batch, 10 Euler steps, against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,B,T,lengths,n,seed", [
+    (160, 1, 344, None, 10, 21),                       # config 1 shape
+    (160, 4, 344, None, 10, 22),                       # config 2, all rows full length (real attention everywhere)
+    (160, 4, 344, [344, 331, 312, 300], 10, 23),       # config 2, bucketed ragged lengths
+    (160, 4, 344, [344, 331, 312, 300], 2, 24),        # config 3 sweep ends
+    (160, 2, 344, None, 50, 25),
+    (160, 2, 1024, None, 10, 26),                      # config 4 regime (multi-tile attention), reduced T for CPU time
+    (160, 2, 1024, [1024, 700], 10, 27),
+    (224, 4, 200, [200, 180, 64, 133], 10, 28),        # config 5: multi-speaker
+])
+def test_ten_step_parity(lj, vctk, cin, B, T, lengths, n, seed):
+    dec, cfg, sd = lj if cin == 160 else vctk
+    mu, mask, z0, spks = O.make_inputs(cfg, B, T, lengths, seed=seed)
+    zr = O.euler_solve(sd, cfg, z0, mu, mask, n, spks)
+    z = dec.solve(_d(z0), _d(mu), _d(mask), n, _d(spks), "euler", use_graph=True).cpu()
+    ma, rl = O.parity_errors(z, zr, mask)
+    print(f"cin={cin} B={B} T={T} n={n}: max-abs {ma:.2e} rel-L2 {rl:.2e}")
+    assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+def test_midpoint_and_graph_equivalence(lj):
+    dec, cfg, sd = lj
+    mu, mask, z0, _ = O.make_inputs(cfg, 2, 64, [64, 37], seed=31)
+    zr = O.euler_solve(sd, cfg, z0, mu, mask, 4, None, "midpoint")
+    za = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "midpoint", use_graph=False)
+    zb = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "midpoint", use_graph=True)
+    zc = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "midpoint", use_graph=True)    # cached graph replay
+    assert torch.equal(za, zb) and torch.equal(zb, zc)                                # bit-stable
+    ma, rl = O.parity_errors(za.cpu(), zr, mask)
+    assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the reference's contract
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,lengths", [(1, 2, None), (2, 4, [4, 1]), (3, 6, [6, 6, 2]), (1, 30, None),
+                                         (5, 34, [34, 33, 2, 17, 1]), (2, 130, [130, 129]), (1, 258, None)])
+def test_small_and_ragged_shapes(lj, B, T, lengths):
+    dec, cfg, sd = lj
+    mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=B * 100 + T)
+    t = torch.linspace(0.0, 0.8, B)
+    ref = O.estimator_forward(sd, cfg, z0, mask, mu, t)
+    out = dec(_d(z0), _d(mask), _d(mu), _d(t)).cpu()
+    ma, rl = O.parity_errors(out, ref, mask)
+    assert ma <= O.TOL_MAX_ABS and rl <= 2 * EST_REL, (ma, rl)       # tiny T: GroupNorm over few frames amplifies rounding
+
+
+def test_arbitrary_mask_and_scalar_t(lj):
+    """Decoder.forward honours any 0/1 mask (holes, a fully padded row), not only prefix masks, and
+    broadcasts a scalar t like the reference's time embedding does."""
+    dec, cfg, sd = lj
+    B, T = 3, 40
+    mu, _, z0, _ = O.make_inputs(cfg, B, T, None, seed=41)
+    g = torch.Generator().manual_seed(42)
+    mask = (torch.rand(B, 1, T, generator=g) > 0.3).float()
+    mask[1] = 1.0
+    ref = O.estimator_forward(sd, cfg, z0, mask, mu, torch.full((B,), 0.25))
+    out = dec(_d(z0), _d(mask), _d(mu), torch.tensor(0.25)).cpu()
+    ma, rl = O.parity_errors(out, ref, mask)
+    assert ma <= O.TOL_MAX_ABS and rl <= EST_REL, (ma, rl)
+
+
+def test_invalid_shapes_raise(lj):
+    dec, cfg, _ = lj
+    from matcha_tts_b200._lib import MttsError
+    z = torch.zeros(1, 80, 33, device="cuda")
+    with pytest.raises(MttsError):                                   # odd T is not supported by the native path
+        dec(z, torch.ones(1, 1, 33, device="cuda"), z, torch.zeros(1, device="cuda"))
+    with pytest.raises(ValueError):
+        dec(z[:, :40], torch.ones(1, 1, 33, device="cuda"), z[:, :40], torch.zeros(1, device="cuda"))
+    with pytest.raises(ValueError):                                   # spks given to a single-speaker estimator
+        dec(z, torch.ones(1, 1, 33, device="cuda"), z, torch.zeros(1, device="cuda"), torch.zeros(1, 64, device="cuda"))
+    with pytest.raises(RuntimeError):
+        dec(z.cpu(), torch.ones(1, 1, 33), z.cpu(), torch.zeros(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config 2: B=64, T=344) -- the oracle is too slow here
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(lj):
+    dec, cfg, sd = lj
+    B, T = 64, 344
+    g = torch.Generator().manual_seed(2)
+    lengths = torch.randint(300, 345, (B,), generator=g)
+    lengths[0] = T
+    lengths[1] = T
+    mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=3)
+    z1 = dec.solve(_d(z0), _d(mu), _d(mask), 10, None, "euler", use_graph=True)
+    z2 = dec.solve(_d(z0), _d(mu), _d(mask), 10, None, "euler", use_graph=True)
+    assert torch.equal(z1, z2)                                          # run-to-run bit-stability
+    assert torch.isfinite(z1).all()
+    assert torch.equal(z1.cpu() * (1 - mask), z0 * (1 - mask))          # padded frames untouched
+    # rows are independent: the same utterances solved in a sub-batch give the same mel (not bit-exact:
+    # the GroupNorm partial sums are grouped by the row's position in the flat tile space)
+    idx = [0, 1, 5, 17, 40, 63]
+    zs = dec.solve(_d(z0[idx]), _d(mu[idx]), _d(mask[idx]), 10, None, "euler", use_graph=False).cpu()
+    ma, rl = O.parity_errors(zs, z1.cpu()[idx], mask[idx])
+    assert ma <= 5e-3 and rl <= 5e-4, (ma, rl)
+    # and the sub-batch itself is checked against the oracle (6 rows x 344 frames x 10 steps)
+    zr = O.euler_solve(sd, cfg, z0[idx], mu[idx], mask[idx], 10)
+    ma, rl = O.parity_errors(zs, zr, mask[idx])
+    assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+def test_cfm_forward_draws_noise_like_reference(lj):
+    """CFM.forward draws z = randn_like(mu) * temperature on mu's device (model.py:1085): the same seed
+    gives the same result as solve_from() on that explicit draw."""
+    from matcha_tts_b200 import CFM
+    dec, cfg, sd = lj
+    cfm = CFM(80, {"solver": "euler", "sigma_min": 1e-4}, estimator=dec)
+    mu, mask, _, _ = O.make_inputs(cfg, 2, 32, [32, 20], seed=51)
+    mu, mask = mu.cuda(), mask.cuda()
+    torch.manual_seed(123)
+    a = cfm(mu, mask, 3, temperature=0.667)
+    torch.manual_seed(123)
+    z = torch.randn_like(mu) * 0.667
+    b = cfm.solve_from(z, mu, mask, 3)
+    assert torch.equal(a, b)
+    ref = O.euler_solve(sd, cfg, z.cpu(), mu.cpu(), mask.cpu(), 3)
+    ma, rl = O.parity_errors(a.cpu(), ref, mask.cpu())
+    assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+def test_synthesize_facade_with_stub_encoder(lj):
+    """MatchaTTS.synthesize wiring (durations -> mask -> path -> mu_y -> native decoder -> denormalize
+    -> crop) around an injected encoder; checked against the same glue run over the oracle."""
+    import types
+    from matcha_tts_b200 import MatchaTTS
+    dec, cfg, sd = lj
+
+    class StubEncoder(torch.nn.Module):
+        def forward(self, x, x_lengths, spks=None):
+            g = torch.Generator().manual_seed(7)
+            B, Tx = x.shape
+            mu = torch.randn(B, 80, Tx, generator=g).to(x.device)
+            logw = (torch.rand(B, 1, Tx, generator=g) * 1.2).to(x.device)
+            x_mask = (torch.arange(Tx, device=x.device)[None, :] < x_lengths[:, None]).unsqueeze(1).float()
+            return mu, logw, x_mask
+
+    enc_p = types.SimpleNamespace(n_feats=80)
+    dp = types.SimpleNamespace(channels=(256, 256), dropout=0.05, attention_head_dim=64, n_blocks=1,
+                               num_mid_blocks=2, num_heads=2, act_fn="snakebeta")
+    m = MatchaTTS(178, 1, 64, enc_p, dp, {"solver": "euler"}, encoder=StubEncoder()).cuda()
+    m.decoder.estimator.load_state_dict(sd)
+    m.mel_mean.fill_(-5.5)
+    m.mel_std.fill_(2.1)
+    x = torch.zeros(2, 9, dtype=torch.long, device="cuda")
+    xl = torch.tensor([9, 6], device="cuda")
+    torch.manual_seed(5)
+    mel, ylen, attn = m.synthesise(x, xl, n_timesteps=4, temperature=0.667)
+    assert mel.shape[0] == 2 and mel.shape[1] == 80 and mel.shape[2] == int(ylen.max())
+    assert attn.shape[:3] == (2, 1, 9)
+    # oracle over the same glue
+    mu, logw, x_mask = StubEncoder()(x.cpu(), xl.cpu())
+    w_ceil = torch.ceil(torch.exp(logw) * x_mask)
+    yl = torch.clamp_min(w_ceil.sum([1, 2]), 1).long()
+    assert torch.equal(yl, ylen.cpu())
+    Tm = O.fix_len_compatibility(int(yl.max()))
+    y_mask = O.sequence_mask(yl, Tm).unsqueeze(1).float()
+    assert torch.allclose(attn.cpu().sum(2)[:, 0, :int(yl.max())].sum(-1), yl.float())     # every valid frame maps to one token
+    mu_y = torch.matmul(attn.cpu().squeeze(1).transpose(1, 2), mu.transpose(1, 2)).transpose(1, 2)
+    torch.manual_seed(5)
+    z0 = (torch.randn(mu_y.shape, device="cuda") * 0.667).cpu()
+    ref = O.euler_solve(sd, cfg, z0, mu_y, y_mask, 4) * 2.1 - 5.5
+    ma, rl = O.parity_errors(mel.cpu(), ref[:, :, :int(yl.max())], y_mask[:, :, :int(yl.max())])
+    assert ma <= 2.1 * O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
