@@ -126,7 +126,8 @@ def _init_param(key: str, shape, spec: Dict[str, tuple]) -> torch.Tensor:
 # native engine: one libmtts handle per (Decoder, device)
 # ----------------------------------------------------------------------------------------------
 def _aligned_buffer(nbytes: int, device, align: int = 1024) -> Tuple[torch.Tensor, int]:
-    buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    with torch.inference_mode(False):
+        buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
     ptr = (buf.data_ptr() + align - 1) // align * align
     return buf, ptr
 
@@ -199,8 +200,11 @@ class _Engine:
         key = (B, T, spks is not None)
         st = self.static.get(key)
         if st is None:
-            st = {"z": torch.empty_like(z), "mu": torch.empty_like(mu), "mask": torch.empty_like(mask),
-                  "spks": torch.empty_like(spks) if spks is not None else None}
+            with torch.inference_mode(False):     # plain tensors: reusable inside and outside inference_mode
+                st = {"z": torch.empty(z.shape, dtype=z.dtype, device=z.device),
+                      "mu": torch.empty(mu.shape, dtype=mu.dtype, device=mu.device),
+                      "mask": torch.empty(mask.shape, dtype=mask.dtype, device=mask.device),
+                      "spks": None if spks is None else torch.empty(spks.shape, dtype=spks.dtype, device=spks.device)}
             self.static[key] = st
         st["z"].copy_(z); st["mu"].copy_(mu); st["mask"].copy_(mask)
         if spks is not None:
