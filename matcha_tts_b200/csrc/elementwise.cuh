@@ -79,7 +79,7 @@ __global__ void prep_x0_kernel(const float* __restrict__ z, const float* __restr
 //        h = (Mish(GN(y)) * m + temb[c]) * m                      model.py:773-775, :786-787
 //   MODE 1 (Block1D #2):  x_r = Mish(GN(y)) * m + res  (NOT masked, :788-789),  a = LayerNorm1(x_r) :735
 // y is the raw conv output (+bias) in fp16; statistics come from the conv epilogue's partial sums.
-// grid = (ceil(Lp/64), B), block = 256 (8 warps, one row per warp per iteration, 8 channels per lane)
+// grid = (ceil(Lp/32), B), block = 128 (4 warps x 8 rows, 4 rows in flight per warp, 8 channels per lane)
 // ---------------------------------------------------------------------------------------------
 struct GnParams {
   const __half* y;
@@ -97,84 +97,133 @@ struct GnParams {
   __half* out2;  // MODE 1: a
 };
 
+constexpr int GN_THREADS = 128;       // 4 warps
+constexpr int GN_ROWS_PER_BLOCK = 32; // 8 rows per warp, 4 in flight at a time
+
 template <int MODE>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) {
   __shared__ float s_mean[8], s_rstd[8];
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 8) {
-    const int g = threadIdx.x;
+  const int c0 = lane * 8, g = lane >> 2;
+  // weights do not depend on the previous kernel: fetch them while it drains
+  float ga[8], be[8], te[8], lg[8], lb[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + c0), g1 = *reinterpret_cast<const float4*>(p.gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p.beta + c0), b1 = *reinterpret_cast<const float4*>(p.beta + c0 + 4);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+    if (MODE == 1) {
+      const float4 l0 = *reinterpret_cast<const float4*>(p.ln_g + c0), l1 = *reinterpret_cast<const float4*>(p.ln_g + c0 + 4);
+      const float4 m0 = *reinterpret_cast<const float4*>(p.ln_b + c0), m1 = *reinterpret_cast<const float4*>(p.ln_b + c0 + 4);
+      lg[0] = l0.x; lg[1] = l0.y; lg[2] = l0.z; lg[3] = l0.w; lg[4] = l1.x; lg[5] = l1.y; lg[6] = l1.z; lg[7] = l1.w;
+      lb[0] = m0.x; lb[1] = m0.y; lb[2] = m0.z; lb[3] = m0.w; lb[4] = m1.x; lb[5] = m1.y; lb[6] = m1.z; lb[7] = m1.w;
+    }
+  }
+  pdl_wait();
+  // finalise the GroupNorm statistics of utterance b: 16 threads per group sum the per-32-row
+  // partials in a fixed order (deterministic), in double to keep E[x^2]-E[x]^2 safe
+  {
+    const int gg = threadIdx.x >> 4, k = threadIdx.x & 15;
     const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
     double s = 0.0, ss = 0.0;
-    for (int sl = 0; sl <= last - first; ++sl) {
-      const float* pp = p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * g;
-      s += (double)pp[0];
-      ss += (double)pp[1];
+    for (int sl = k; sl <= last - first; sl += 16) {
+      const float2 pp = *reinterpret_cast<const float2*>(p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * gg);
+      s += (double)pp.x;
+      ss += (double)pp.y;
     }
-    const double n = 32.0 * (double)p.L;
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = (float)mean;
-    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (k == 0) {
+      const double n = 32.0 * (double)p.L;
+      const double mean = s / n;
+      double var = ss / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[gg] = (float)mean;
+      s_rstd[gg] = (float)(1.0 / sqrt(var + 1e-5));
+    }
   }
   __syncthreads();
-  const int c0 = lane * 8, g = lane >> 2;
   const float mean = s_mean[g], rstd = s_rstd[g];
-  float ga[8], be[8], te[8], lg[8], lb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    ga[j] = p.gamma[c0 + j] * rstd;
-    be[j] = p.beta[c0 + j] - mean * ga[j];
-    te[j] = (MODE == 0 && p.temb) ? p.temb[(size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0 + j] : 0.f;
-    if (MODE == 1) { lg[j] = p.ln_g[c0 + j]; lb[j] = p.ln_b[c0 + j]; }
+    ga[j] *= rstd;
+    be[j] = be[j] - mean * ga[j];
+    te[j] = 0.f;
   }
-  const int tend = min(p.Lp, (int)(blockIdx.x + 1) * 64);
-  for (int t = blockIdx.x * 64 + warp; t < tend; t += 8) {
-    const size_t row = (size_t)b * p.Lp + t;
-    uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
-    if (t < p.L) {
-      const float m = p.rowmask[row];
-      const uint4 yv = *reinterpret_cast<const uint4*>(p.y + row * 256 + c0);
-      float v[8];
-      float2 f;
-      f = unpack_h2(yv.x); v[0] = f.x; v[1] = f.y;
-      f = unpack_h2(yv.y); v[2] = f.x; v[3] = f.y;
-      f = unpack_h2(yv.z); v[4] = f.x; v[5] = f.y;
-      f = unpack_h2(yv.w); v[6] = f.x; v[7] = f.y;
-      if (MODE == 0) {
+  if (MODE == 0 && p.temb) {
+    const float* tp = p.temb + (size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0;
+    const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+    te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+  }
+  const int tw0 = blockIdx.x * GN_ROWS_PER_BLOCK + warp * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m + te[j]) * m;
-      } else {
-        const uint4 rv = *reinterpret_cast<const uint4*>(p.res + row * 256 + c0);
-        float r[8];
-        f = unpack_h2(rv.x); r[0] = f.x; r[1] = f.y;
-        f = unpack_h2(rv.y); r[2] = f.x; r[3] = f.y;
-        f = unpack_h2(rv.z); r[4] = f.x; r[5] = f.y;
-        f = unpack_h2(rv.w); r[6] = f.x; r[7] = f.y;
-        float s = 0.f, ss = 0.f;
+  for (int batch = 0; batch < 2; ++batch) {
+    uint4 yv[4], rv[4];
+    float m[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m + r[j];
-          s += v[j];
-          ss = fmaf(v[j], v[j], ss);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, off);
-          ss += __shfl_xor_sync(0xffffffffu, ss, off);
-        }
-        const float lmean = s * (1.f / 256.f);
-        const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
-        o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
+    for (int i = 0; i < 4; ++i) {
+      const int t = tw0 + batch * 4 + i;
+      const size_t row = (size_t)b * p.Lp + t;
+      yv[i] = make_uint4(0, 0, 0, 0);
+      rv[i] = make_uint4(0, 0, 0, 0);
+      m[i] = 0.f;
+      if (t < p.L) {
+        yv[i] = ldg128(p.y + row * 256 + c0);
+        if (MODE == 1) rv[i] = ldg128(p.res + row * 256 + c0);
+        m[i] = p.rowmask[row];
       }
-      o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
     }
-    *reinterpret_cast<uint4*>(p.out + row * 256 + c0) = o;  // guard rows are written as zeros
-    if (MODE == 1) *reinterpret_cast<uint4*>(p.out2 + row * 256 + c0) = o2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = tw0 + batch * 4 + i;
+      if (t >= p.Lp) continue;   // warp-uniform
+      const size_t row = (size_t)b * p.Lp + t;
+      uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
+      if (t < p.L) {
+        float v[8];
+        float2 f;
+        f = unpack_h2(yv[i].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_h2(yv[i].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_h2(yv[i].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_h2(yv[i].w); v[6] = f.x; v[7] = f.y;
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + te[j]) * m[i];
+        } else {
+          float r[8];
+          f = unpack_h2(rv[i].x); r[0] = f.x; r[1] = f.y;
+          f = unpack_h2(rv[i].y); r[2] = f.x; r[3] = f.y;
+          f = unpack_h2(rv[i].z); r[4] = f.x; r[5] = f.y;
+          f = unpack_h2(rv[i].w); r[6] = f.x; r[7] = f.y;
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + r[j];
+            s += v[j];
+            ss = fmaf(v[j], v[j], ss);
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+          }
+          const float lmean = s * (1.f / 256.f);
+          const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
+          o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
+        }
+        o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+      }
+      stg128(p.out + row * 256 + c0, o);  // guard rows are written as zeros
+      if (MODE == 1) stg128(p.out2 + row * 256 + c0, o2);
+    }
   }
 }
 

@@ -9,11 +9,16 @@
 // `torch.cat` along channels is a second tensor map in the K loop.  Weights are pre-packed
 // [N, Ktot] K-major fp16.  Accumulation is fp32 in TMEM.
 //
-// Warp roles (192 threads, persistent over tiles, 1 CTA / SM):
+// Warp roles (320 threads, persistent over tiles, 1 CTA / SM):
 //   warp 0   TMA producer   (A tile 128x64 + B tile BNx64 per stage, 128B swizzle, mbarrier tx)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (4 x K16 per stage), tcgen05.commit
-//   warps 2-5 epilogue: tcgen05.ld (one accumulator row per thread), fused math, smem-staged
-//             coalesced stores.  Two accumulator stages in TMEM overlap epilogue(i) with mma(i+1).
+//   warps 2-9 epilogue: two warps per TMEM lane quarter, each owning half of the tile's columns;
+//             tcgen05.ld (one accumulator row per thread, 32 columns at a time), fused math,
+//             swizzled smem staging -> 64-byte-per-row coalesced global stores; residual tiles are
+//             prefetched into registers one chunk ahead.  Two accumulator stages in TMEM overlap
+//             epilogue(i) with mma(i+1).
+// Every launch uses programmatic dependent launch: the prologue (barriers, TMEM alloc, descriptor
+// prefetch) runs while the previous kernel drains; griddepcontrol.wait precedes the first global access.
 //
 // Fused epilogues (reference file:line each one replaces is listed in DESIGN.md):
 //   EPI_STATS  +bias, fp16 store, deterministic GroupNorm partial sums per (utterance, group)
@@ -32,10 +37,10 @@ namespace mtts {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;        // 320
 constexpr int GEMM_MAX_SEGS = 9;
-constexpr int GEMM_STAGE_PITCH = 144;                          // bytes per staged row (128 + 16 pad)
-constexpr int GEMM_STAGING_BYTES = 32 * GEMM_STAGE_PITCH;      // per epilogue warp
+constexpr int GEMM_STAGING_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 32 fp16, swizzled
 
 enum { EPI_STATS = 0, EPI_PLAIN = 1, EPI_LN = 2, EPI_SNAKE = 3, EPI_QKV = 4, EPI_FINAL = 5 };
 
@@ -93,55 +98,61 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int PAR_BYTES = 3 * BN * 4;
-  static constexpr int TOTAL = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * GEMM_STAGING_BYTES + PAR_BYTES + 256;
+  static constexpr int RED_BYTES = GEMM_BM * 2 * 8;  // LayerNorm partial (sum, sumsq) per row and column half
+  static constexpr int TOTAL = 1024 /*align slack*/ + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_BYTES +
+                               PAR_BYTES + RED_BYTES + 256;
 };
 
 // ---- epilogue helpers -------------------------------------------------------------------------
-// store 64 fp32 values of "my" row as fp16 through the warp's staging buffer, coalesced 128 B / row
-__device__ __forceinline__ void epi_store_h64(uint8_t* st, int lane, const float* v, __half* gtile, int ld,
+// Per-warp staging tile: 32 rows x 64 B (32 fp16); 16-byte unit u of row r lives at
+// r*64 + ((u ^ ((r >> 1) & 3)) << 4): conflict-free both for "thread = row" accesses and for the
+// coalesced pattern (8 rows x 64 B per instruction: lane -> row it*8 + lane/4, unit lane%4).
+__device__ __forceinline__ uint32_t epi_st_addr(uint32_t st, int row, int unit) {
+  return st + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4);
+}
+// store 32 fp32 values of "my" row as fp16, coalesced 64 B per row
+__device__ __forceinline__ void epi_store_h32(uint32_t st, int lane, const float* v, __half* gtile, int ld,
                                               int rows_valid) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 u;
-    u.x = pack_h2(v[8 * j + 0], v[8 * j + 1]);
-    u.y = pack_h2(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack_h2(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack_h2(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(st + lane * GEMM_STAGE_PITCH + j * 16) = u;
-  }
+  for (int j = 0; j < 4; ++j)
+    sts128(epi_st_addr(st, lane, j), make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7])));
   __syncwarp();
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    int row = it * 4 + (lane >> 3), c = lane & 7;
-    uint4 u = *reinterpret_cast<const uint4*>(st + row * GEMM_STAGE_PITCH + c * 16);
-    if (row < rows_valid) *reinterpret_cast<uint4*>(gtile + (size_t)row * ld + c * 8) = u;
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), unit = lane & 3;
+    const uint4 u = lds128(epi_st_addr(st, row, unit));
+    if (row < rows_valid) stg128(gtile + (size_t)row * ld + unit * 8, u);
   }
   __syncwarp();
 }
-// add 64 fp16 residual values of "my" row (coalesced global read through the staging buffer)
-__device__ __forceinline__ void epi_add_resid_h64(uint8_t* st, int lane, float* v, const __half* gtile, int ld,
-                                                  int rows_valid) {
+// issue the coalesced loads of a 32x32 fp16 residual tile (consumed later by epi_resid_add)
+__device__ __forceinline__ void epi_resid_issue(uint4 (&rr)[4], int lane, const __half* gtile, int ld, int rows_valid) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    int row = it * 4 + (lane >> 3), c = lane & 7;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (row < rows_valid) u = *reinterpret_cast<const uint4*>(gtile + (size_t)row * ld + c * 8);
-    *reinterpret_cast<uint4*>(st + row * GEMM_STAGE_PITCH + c * 16) = u;
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), unit = lane & 3;
+    rr[it] = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) rr[it] = ldg128(gtile + (size_t)row * ld + unit * 8);
   }
+}
+__device__ __forceinline__ void epi_resid_add(uint32_t st, int lane, const uint4 (&rr)[4], float* v) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) sts128(epi_st_addr(st, it * 8 + (lane >> 2), lane & 3), rr[it]);
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 u = *reinterpret_cast<const uint4*>(st + lane * GEMM_STAGE_PITCH + j * 16);
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = lds128(epi_st_addr(st, lane, j));
     float2 f;
     f = unpack_h2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
     f = unpack_h2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
     f = unpack_h2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
     f = unpack_h2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
   }
-  __syncwarp();
+  // the next staging writes of this thread target its own row only; cross-row reuse is ordered by
+  // the __syncwarp()s inside epi_store_h32
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -155,8 +166,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;
-  float* s_par = reinterpret_cast<float*>(staging + 4 * GEMM_STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + SM::PAR_BYTES);
+  float* s_par = reinterpret_cast<float*>(staging + GEMM_EPI_WARPS * GEMM_STAGING_BYTES);
+  uint8_t* s_red = reinterpret_cast<uint8_t*>(s_par) + SM::PAR_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + SM::RED_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
@@ -166,6 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();  // the next kernel may start its prologue; it still waits for our completion
+
   int total_chunks = 0;
   for (int s = 0; s < p.num_segs; ++s) total_chunks += p.seg[s].nchunks;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -173,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -184,6 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();  // everything below touches memory the previous kernel may still be using
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -244,9 +260,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // ===================================== epilogue =========================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* st = staging + (warp - 2) * GEMM_STAGING_BYTES;
-    const int et = threadIdx.x - 64;  // 0..127
+    constexpr int CW = BN / 2;    // columns per epilogue warp
+    constexpr int NCH = CW / 32;  // 32-column chunks per warp
+    const int ew = warp - 2;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int hcol = ew >> 2;     // which half of the tile's columns
+    const int cbase = hcol * CW;
+    const uint32_t st = smem_u32(staging + ew * GEMM_STAGING_BYTES);
+    const uint32_t spar = smem_u32(s_par);
+    const int et = threadIdx.x - 64;  // 0..255
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -258,130 +280,181 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int rows_valid = min(32, p.M - rw0);  // may be <= 0
       const bool row_ok = row < p.M;
 
-      // per-tile column parameters -> smem (all 4 epilogue warps)
+      // per-tile column parameters -> smem (all epilogue warps)
       epi_bar_sync();
-      for (int i = et; i < BN; i += 128) {
+      for (int i = et; i < BN; i += 32 * GEMM_EPI_WARPS) {
         s_par[i] = p.bias ? p.bias[n0 + i] : 0.f;
         if constexpr (EPI == EPI_LN) { s_par[BN + i] = p.ln_g[n0 + i]; s_par[2 * BN + i] = p.ln_b[n0 + i]; }
         if constexpr (EPI == EPI_SNAKE) { s_par[BN + i] = p.sn_a[n0 + i]; s_par[2 * BN + i] = p.sn_ib[n0 + i]; }
       }
       epi_bar_sync();
 
-      if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
-      __syncwarp();
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + cbase;
 
       if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_LN || EPI == EPI_SNAKE) {
+        const bool has_res = (EPI == EPI_LN) || (EPI == EPI_PLAIN && p.resid != nullptr);
+        const __half* rbase = has_res ? p.resid + (size_t)rw0 * p.ldr + n0 + cbase : nullptr;
+        uint4 rr[4];
+        if (has_res) epi_resid_issue(rr, lane, rbase, p.ldr, rows_valid);
         float mrow = 1.f;
         if constexpr (EPI == EPI_PLAIN) if (p.rowmask && row_ok) mrow = p.rowmask[(size_t)row * p.mask_mul + n_tile * p.mask_nstep];
         int myb = -1;
         if constexpr (EPI == EPI_STATS) if (row_ok) myb = p.rowb[row];
-        float gs[(EPI == EPI_STATS) ? 16 : 1];
+
+        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        __syncwarp();
+        tc_fence_after();
+
+        float gs[(EPI == EPI_STATS) ? 2 * NCH : 1];
         float lsum = 0.f, lsq = 0.f;
-#pragma unroll 1
-        for (int u = 0; u < BN / 64; ++u) {
-          float v[64];
-          tmem_ld32(taddr + u * 64, v);
-          tmem_ld32(taddr + u * 64 + 32, v + 32);
+        __half* obase = p.out + (size_t)rw0 * p.ldo + n0 + cbase;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] += s_par[u * 64 + j];
-          if ((EPI == EPI_PLAIN && p.resid != nullptr) || EPI == EPI_LN)
-            epi_add_resid_h64(st, lane, v, p.resid + (size_t)rw0 * p.ldr + n0 + u * 64, p.ldr, rows_valid);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = lds_f4(spar + (cbase + c * 32 + 4 * j) * 4);
+            v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+          if (has_res) {
+            epi_resid_add(st, lane, rr, v);
+            if (c + 1 < NCH) epi_resid_issue(rr, lane, rbase + (c + 1) * 32, p.ldr, rows_valid);
+          }
           if constexpr (EPI == EPI_SNAKE) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              float s = sinf(v[j] * s_par[BN + u * 64 + j]);
-              v[j] = fmaf(s * s, s_par[2 * BN + u * 64 + j], v[j]);
+            for (int j = 0; j < 8; ++j) {
+              const float4 a4 = lds_f4(spar + (BN + cbase + c * 32 + 4 * j) * 4);
+              const float4 i4 = lds_f4(spar + (2 * BN + cbase + c * 32 + 4 * j) * 4);
+              float s;
+              s = fast_sin(v[4 * j + 0] * a4.x); v[4 * j + 0] = fmaf(s * s, i4.x, v[4 * j + 0]);
+              s = fast_sin(v[4 * j + 1] * a4.y); v[4 * j + 1] = fmaf(s * s, i4.y, v[4 * j + 1]);
+              s = fast_sin(v[4 * j + 2] * a4.z); v[4 * j + 2] = fmaf(s * s, i4.z, v[4 * j + 2]);
+              s = fast_sin(v[4 * j + 3] * a4.w); v[4 * j + 3] = fmaf(s * s, i4.w, v[4 * j + 3]);
             }
           }
-          if constexpr (EPI == EPI_STATS) {
-            float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+          if constexpr (EPI == EPI_STATS) {  // one 32-column chunk == one GroupNorm group
+            float a0 = 0.f, b0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { a0 += v[j]; b0 = fmaf(v[j], v[j], b0); }
-#pragma unroll
-            for (int j = 32; j < 64; ++j) { a1 += v[j]; b1 = fmaf(v[j], v[j], b1); }
-#pragma unroll
-            for (int uu = 0; uu < BN / 64; ++uu)
-              if (uu == u) { gs[4 * uu + 0] = a0; gs[4 * uu + 1] = b0; gs[4 * uu + 2] = a1; gs[4 * uu + 3] = b1; }
+            gs[2 * c] = a0; gs[2 * c + 1] = b0;
           }
           if constexpr (EPI == EPI_LN) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { lsum += v[j]; lsq = fmaf(v[j], v[j], lsq); }
-            tmem_st32(taddr + u * 64, v);
-            tmem_st32(taddr + u * 64 + 32, v + 32);
+            for (int j = 0; j < 32; ++j) { lsum += v[j]; lsq = fmaf(v[j], v[j], lsq); }
+            tmem_st32(taddr + c * 32, v);
           }
           if constexpr (EPI == EPI_PLAIN) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] *= mrow;
+            for (int j = 0; j < 32; ++j) v[j] *= mrow;
           }
-          epi_store_h64(st, lane, v, p.out + (size_t)rw0 * p.ldo + n0 + u * 64, p.ldo, rows_valid);
+          epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
         }
         if constexpr (EPI == EPI_STATS) {
-          // deterministic per-(utterance, group) partial sums of this warp's 32 rows
-          float* sf = reinterpret_cast<float*>(st);
-          int* sb = reinterpret_cast<int*>(st + 32 * 17 * 4);
+          // deterministic per-(utterance, group) partial sums of this warp's 32 rows x 4 groups:
+          // slot = 32-row block index relative to the utterance's first block, 16 floats per slot
+          // (group g -> [2g] sum, [2g+1] sum of squares); this warp owns groups hcol*4 .. hcol*4+3.
+          const int wb = rw0 >> 5;
+          const int b0 = __shfl_sync(0xffffffffu, myb, 0);
+          if (__all_sync(0xffffffffu, myb == b0)) {
+            if (b0 >= 0) {  // uniform
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sf[lane * 17 + j] = gs[j];
-          sb[lane] = myb;
-          __syncwarp();
-          if (lane < 16) {
-            int cur = -1;
-            float acc = 0.f;
-            const int wb = rw0 >> 5;
-            for (int i = 0; i < 32; ++i) {
-              int bi = sb[i];
-              if (bi != cur) {
-                if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + lane] = acc;
-                cur = bi;
-                acc = 0.f;
+              for (int j = 0; j < 2 * NCH; ++j) {
+                float x = gs[j];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                gs[j] = x;
               }
-              acc += sf[i * 17 + lane];
+              if (lane == 0) {
+                float* dst = p.stats_part + ((size_t)b0 * p.S + (wb - ((b0 * p.Lp) >> 5))) * 16 + hcol * 2 * NCH;
+#pragma unroll
+                for (int j = 0; j < 2 * NCH; ++j) dst[j] = gs[j];
+              }
             }
-            if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + lane] = acc;
+          } else {  // utterance boundary inside the warp's rows: serial, fixed order
+            const uint32_t sf = st;                 // [32][9] floats
+            const uint32_t sb = st + 32 * 9 * 4;    // [32] ints
+#pragma unroll
+            for (int j = 0; j < 2 * NCH; ++j) sts_f32(sf + (lane * 9 + j) * 4, gs[j]);
+            sts_u32(sb + lane * 4, (uint32_t)myb);
+            __syncwarp();
+            if (lane < 2 * NCH) {
+              int cur = -1;
+              float acc = 0.f;
+              for (int i = 0; i < 32; ++i) {
+                const int bi = (int)lds_u32(sb + i * 4);
+                if (bi != cur) {
+                  if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + hcol * 2 * NCH + lane] = acc;
+                  cur = bi;
+                  acc = 0.f;
+                }
+                acc += lds_f32(sf + (i * 9 + lane) * 4);
+              }
+              if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + hcol * 2 * NCH + lane] = acc;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if constexpr (EPI == EPI_LN) {
+          // LayerNorm over the full BN-wide row: combine the two column halves through smem
+          const uint32_t red = smem_u32(s_red);
+          const int trow = q * 32 + lane;
+          sts_f32(red + (trow * 2 + hcol) * 8, lsum);
+          sts_f32(red + (trow * 2 + hcol) * 8 + 4, lsq);
           tmem_st_wait();
-          const float mean = lsum * (1.f / BN);
-          const float var = fmaxf(lsq * (1.f / BN) - mean * mean, 0.f);
+          epi_bar_sync();
+          const float osum = lds_f32(red + (trow * 2 + (hcol ^ 1)) * 8);
+          const float osq = lds_f32(red + (trow * 2 + (hcol ^ 1)) * 8 + 4);
+          // add in a fixed (half 0, half 1) order so both warps of a pair see bit-identical statistics
+          const float tsum = hcol ? (osum + lsum) : (lsum + osum);
+          const float tsq = hcol ? (osq + lsq) : (lsq + osq);
+          const float mean = tsum * (1.f / BN);
+          const float var = fmaxf(tsq * (1.f / BN) - mean * mean, 0.f);
           const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll 1
-          for (int u = 0; u < BN / 64; ++u) {
-            float v[64];
-            tmem_ld32(taddr + u * 64, v);
-            tmem_ld32(taddr + u * 64 + 32, v + 32);
+          __half* o2 = p.out2 + (size_t)rw0 * p.ldo + n0 + cbase;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              v[j] = fmaf((v[j] - mean) * rstd, s_par[BN + u * 64 + j], s_par[2 * BN + u * 64 + j]);
-            epi_store_h64(st, lane, v, p.out2 + (size_t)rw0 * p.ldo + n0 + u * 64, p.ldo, rows_valid);
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = lds_f4(spar + (BN + cbase + c * 32 + 4 * j) * 4);
+              const float4 b4 = lds_f4(spar + (2 * BN + cbase + c * 32 + 4 * j) * 4);
+              v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, g4.x, b4.x);
+              v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, g4.y, b4.y);
+              v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, g4.z, b4.z);
+              v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, g4.w, b4.w);
+            }
+            epi_store_h32(st, lane, v, o2 + c * 32, p.ldo, rows_valid);
           }
         }
       } else if constexpr (EPI == EPI_QKV) {
+        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        __syncwarp();
+        tc_fence_after();
         if (n_tile < 2) {
-          __half* dst = n_tile == 0 ? p.q : p.k;
-#pragma unroll 1
-          for (int u = 0; u < BN / 64; ++u) {
-            float v[64];
-            tmem_ld32(taddr + u * 64, v);
-            tmem_ld32(taddr + u * 64 + 32, v + 32);
+          __half* dst = (n_tile == 0 ? p.q : p.k) + (size_t)rw0 * BN + cbase;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
-            epi_store_h64(st, lane, v, dst + (size_t)rw0 * BN + u * 64, BN, rows_valid);
+            epi_store_h32(st, lane, v, dst + c * 32, BN, rows_valid);
           }
         } else {
           const int b = row_ok ? p.rowb[row] : -1;
           const int t = row - b * p.Lp;
-#pragma unroll 1
-          for (int u = 0; u < BN / 32; ++u) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
             float v[32];
-            tmem_ld32(taddr + u * 32, v);
+            tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
             if (b >= 0) {
-              // column c = u*32 + j -> head c/64, dim c%64 ; lanes = consecutive frames -> coalesced
-              __half* dst = p.vt + ((size_t)(b * 2 + (u >> 1)) * 64 + (u & 1) * 32) * p.Lpad + t;
+              // tile column cc = cbase + c*32 + j -> head cc/64, dim cc%64 ; lanes = consecutive frames
+              const int cc = cbase + c * 32;
+              __half* dst = p.vt + ((size_t)(b * 2 + (cc >> 6)) * 64 + (cc & 63)) * p.Lpad + t;
 #pragma unroll
               for (int j = 0; j < 32; ++j) dst[(size_t)j * p.Lpad] = __float2half_rn(v[j]);
             }
@@ -391,31 +464,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b = row_ok ? p.rowb[row] : -1;
         const int t = row - b * p.Lp;
         const float m = (b >= 0) ? p.rowmask[row] : 0.f;
-#pragma unroll 1
-        for (int u = 0; u < 3; ++u) {  // 80 valid columns = 32 + 32 + 16
-          float v[32];
-          tmem_ld32(taddr + u * 32, v);
-          tmem_ld_wait();
-          if (b >= 0) {
-            const int nj = (u == 2) ? (p.n_valid - 64) : 32;
+        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        __syncwarp();
+        tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nj) {
-                const size_t idx = ((size_t)b * p.n_valid + u * 32 + j) * p.T + t;
-                float o = (v[j] + s_par[u * 32 + j]) * m;
-                o = p.zbase ? fmaf(p.zscale, o, p.zbase[idx]) : o;
-                p.zout[idx] = o;
-                v[j] = o * m;
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = cbase + c * 32;
+          const int nj = min(32, p.n_valid - col0);  // warp-uniform
+          if (nj > 0) {
+            float v[32], zb[32];
+            tmem_ld32(taddr + c * 32, v);
+            const size_t idx0 = ((size_t)max(b, 0) * p.n_valid + col0) * p.T + t;
+            // all state loads are issued before the first store (zout may alias zbase)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) zb[j] = (b >= 0 && p.zbase != nullptr && j < nj) ? p.zbase[idx0 + (size_t)j * p.T] : 0.f;
+            tmem_ld_wait();
+            if (b >= 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float o = fmaf(p.zscale, (v[j] + lds_f32(spar + (col0 + j) * 4)) * m, zb[j]);
+                v[j] = o;
               }
-            }
-            if (p.x0) {
-              uint4* xd = reinterpret_cast<uint4*>(p.x0 + (size_t)row * p.ldx0 + u * 32);
-              const int nv = nj / 8;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < nv)
-                  xd[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
-                                     pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
+              for (int j = 0; j < 32; ++j)
+                if (j < nj) p.zout[idx0 + (size_t)j * p.T] = v[j];
+              if (p.x0) {
+                uint4* xd = reinterpret_cast<uint4*>(p.x0 + (size_t)row * p.ldx0 + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (8 * j < nj)
+                    xd[j] = make_uint4(pack_h2(v[8 * j] * m, v[8 * j + 1] * m), pack_h2(v[8 * j + 2] * m, v[8 * j + 3] * m),
+                                       pack_h2(v[8 * j + 4] * m, v[8 * j + 5] * m), pack_h2(v[8 * j + 6] * m, v[8 * j + 7] * m));
+              }
             }
           }
         }

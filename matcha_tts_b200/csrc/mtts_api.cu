@@ -9,6 +9,8 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/mtts.h"
@@ -141,6 +143,7 @@ struct MttsHandle {
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
   int launch_count = 0, launch_limit = -1;
+  bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   // optional per-launch device timing (CUDA events on the launching stream)
   bool profiling = false;
   cudaStream_t prof_stream = nullptr;
@@ -400,6 +403,22 @@ static void launched(MttsHandle* h) {
   if (h->profiling) prof_mark(h);
 }
 
+// Launch with (optional) programmatic stream serialization: the kernel may start while its
+// predecessor drains; every kernel of the solve executes griddepcontrol.wait before touching
+// global memory (ptx.cuh).  Works both eagerly and under stream capture (programmatic graph edges).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (h->use_pdl && !h->profiling) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BN, int EPI>
 static int set_gemm_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -413,8 +432,7 @@ static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& 
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(a0, a1, wmap, p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, stream, a0, a1, wmap, p));
   launched(h);
   return 0;
 }
@@ -470,14 +488,14 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     p.n_tiles = 1; p.bias = F(sw.res_b); p.out = H(w.res);
     if (int e = launch_gemm<256, EPI_PLAIN>(h, in0, in1, sw.m_res, p, stream, fr * C * ci_real)) return e;
   }
-  const dim3 gn_grid((lc.Lp + 63) / 64, w.B);
+  const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
   {
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
@@ -492,7 +510,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
     g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<1><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // q | k | v^T
   {
@@ -507,8 +525,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
     ap.vt = H(w.vt); ap.out = H(w.o);
     dim3 grid((lc.L + 127) / 128, 2, w.B);
-    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(lm.q, lm.k, lm.vt, ap);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
     launched(h);
   }
   // x_a = x_r + o Wo^T + b ; c = LN3(x_a)
@@ -602,8 +619,8 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
-    const dim3 gn_grid((lT.Lp + 63) / 64, w.B);
-    if (can_launch(h, MTTS_KIND_NORM)) { gn_apply_kernel<0><<<gn_grid, 256, 0, stream>>>(g); CUDA_TRY(cudaGetLastError()); launched(h); }
+    const dim3 gn_grid((lT.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -685,6 +702,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->cinp = (int)align_up(cfg->in_channels, 64);
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
+  if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {

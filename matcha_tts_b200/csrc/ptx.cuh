@@ -157,6 +157,54 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the solve is launched with programmaticStreamSerialization: its prologue
+// (barrier init, TMEM alloc, descriptor prefetch) may overlap the previous kernel's tail.
+// pdl_wait() returns once the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------ explicit shared-space access
+// (addresses from smem_u32(); avoids generic ST.E/LD.E when the pointer provenance is lost)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ------------------------------------------------------------------ small math helpers
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);   // round-to-nearest; values here are O(1..1e2), far from 65504
@@ -173,6 +221,16 @@ __device__ __forceinline__ float mish_f(float x) {
   float e = __expf(x);
   float w = e * (e + 2.f);
   return x * __fdividef(w, w + 2.f);
+}
+
+
+// sin(x) for the SnakeBeta epilogue: two-constant Cody-Waite reduction to [-pi, pi] followed by the
+// SFU sine (abs error ~5e-7 there; the result is rounded to fp16 right after).  Valid for |x| << 1e5.
+__device__ __forceinline__ float fast_sin(float x) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);      // 2*pi rounded to fp32
+  r = fmaf(k, 1.7484556000744883e-7f, r);          // 2*pi - fp32(2*pi) = -1.7484556e-7
+  return __sinf(r);
 }
 
 }  // namespace mtts

@@ -258,7 +258,10 @@ def test_synthesize_facade_with_stub_encoder(lj):
     assert torch.allclose(attn.cpu().sum(2)[:, 0, :int(yl.max())].sum(-1), yl.float())     # every valid frame maps to one token
     mu_y = torch.matmul(attn.cpu().squeeze(1).transpose(1, 2), mu.transpose(1, 2)).transpose(1, 2)
     torch.manual_seed(5)
-    z0 = (torch.randn(mu_y.shape, device="cuda") * 0.667).cpu()
+    # the reference draws randn_like(mu_y) (model.py:1085) and mu_y is a transposed view of a
+    # (B, T, 80) matmul result (model.py:1288-1289), so the noise is laid out in (B, T, 80) memory order
+    Bz, Cz, Tz = mu_y.shape
+    z0 = (torch.randn(Bz, Tz, Cz, device="cuda").transpose(1, 2) * 0.667).cpu().contiguous()
     ref = O.euler_solve(sd, cfg, z0, mu_y, y_mask, 4) * 2.1 - 5.5
     ma, rl = O.parity_errors(mel.cpu(), ref[:, :, :int(yl.max())], y_mask[:, :, :int(yl.max())])
     assert ma <= 2.1 * O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
