@@ -79,7 +79,7 @@ __global__ void prep_x0_kernel(const float* __restrict__ z, const float* __restr
 //        h = (Mish(GN(y)) * m + temb[c]) * m                      model.py:773-775, :786-787
 //   MODE 1 (Block1D #2):  x_r = Mish(GN(y)) * m + res  (NOT masked, :788-789),  a = LayerNorm1(x_r) :735
 // y is the raw conv output (+bias) in fp16; statistics come from the conv epilogue's partial sums.
-// grid = (ceil(Lp/32), B), block = 128 (4 warps x 8 rows, 4 rows in flight per warp, 8 channels per lane)
+// grid = (ceil(Lp/16), B), block = 128 (4 warps x 4 rows, every load issued up front, 8 channels per lane)
 // ---------------------------------------------------------------------------------------------
 struct GnParams {
   const __half* y;
@@ -98,7 +98,7 @@ struct GnParams {
 };
 
 constexpr int GN_THREADS = 128;       // 4 warps
-constexpr int GN_ROWS_PER_BLOCK = 32; // 8 rows per warp, 4 in flight at a time
+constexpr int GN_ROWS_PER_BLOCK = 16; // 4 rows per warp, all in flight at once
 
 template <int MODE>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) {
@@ -122,8 +122,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
     }
   }
   pdl_wait();
-  // finalise the GroupNorm statistics of utterance b: 16 threads per group sum the per-32-row
-  // partials in a fixed order (deterministic), in double to keep E[x^2]-E[x]^2 safe
+  // 1) issue every global load of this block up front (rows, time embedding, statistics partials):
+  //    one memory round trip instead of three dependent ones
+  const int tw0 = blockIdx.x * GN_ROWS_PER_BLOCK + warp * 4;
+  uint4 yv[4], rv[4];
+  float m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = tw0 + i;
+    const size_t row = (size_t)b * p.Lp + t;
+    yv[i] = make_uint4(0, 0, 0, 0);
+    rv[i] = make_uint4(0, 0, 0, 0);
+    m[i] = 0.f;
+    if (t < p.L) {
+      yv[i] = ldg128(p.y + row * 256 + c0);
+      if (MODE == 1) rv[i] = ldg128(p.res + row * 256 + c0);
+      m[i] = p.rowmask[row];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) te[j] = 0.f;
+  if (MODE == 0 && p.temb) {
+    const float* tp = p.temb + (size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0;
+    const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+    te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+  }
+  // 2) finalise the GroupNorm statistics of utterance b: 16 threads per group sum the per-32-row
+  //    partials in a fixed order (deterministic), in double to keep E[x^2]-E[x]^2 safe
   {
     const int gg = threadIdx.x >> 4, k = threadIdx.x & 15;
     const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
@@ -153,77 +178,53 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   for (int j = 0; j < 8; ++j) {
     ga[j] *= rstd;
     be[j] = be[j] - mean * ga[j];
-    te[j] = 0.f;
   }
-  if (MODE == 0 && p.temb) {
-    const float* tp = p.temb + (size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0;
-    const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-    te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-  }
-  const int tw0 = blockIdx.x * GN_ROWS_PER_BLOCK + warp * 8;
+  // 3) normalise, Mish, mask (+temb | +res, LayerNorm), store
 #pragma unroll
-  for (int batch = 0; batch < 2; ++batch) {
-    uint4 yv[4], rv[4];
-    float m[4];
+  for (int i = 0; i < 4; ++i) {
+    const int t = tw0 + i;
+    if (t >= p.Lp) continue;   // warp-uniform
+    const size_t row = (size_t)b * p.Lp + t;
+    uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
+    if (t < p.L) {
+      float v[8];
+      float2 f;
+      f = unpack_h2(yv[i].x); v[0] = f.x; v[1] = f.y;
+      f = unpack_h2(yv[i].y); v[2] = f.x; v[3] = f.y;
+      f = unpack_h2(yv[i].z); v[4] = f.x; v[5] = f.y;
+      f = unpack_h2(yv[i].w); v[6] = f.x; v[7] = f.y;
+      if (MODE == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = tw0 + batch * 4 + i;
-      const size_t row = (size_t)b * p.Lp + t;
-      yv[i] = make_uint4(0, 0, 0, 0);
-      rv[i] = make_uint4(0, 0, 0, 0);
-      m[i] = 0.f;
-      if (t < p.L) {
-        yv[i] = ldg128(p.y + row * 256 + c0);
-        if (MODE == 1) rv[i] = ldg128(p.res + row * 256 + c0);
-        m[i] = p.rowmask[row];
-      }
-    }
+        for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + te[j]) * m[i];
+      } else {
+        float r[8];
+        f = unpack_h2(rv[i].x); r[0] = f.x; r[1] = f.y;
+        f = unpack_h2(rv[i].y); r[2] = f.x; r[3] = f.y;
+        f = unpack_h2(rv[i].z); r[4] = f.x; r[5] = f.y;
+        f = unpack_h2(rv[i].w); r[6] = f.x; r[7] = f.y;
+        float s = 0.f, ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = tw0 + batch * 4 + i;
-      if (t >= p.Lp) continue;   // warp-uniform
-      const size_t row = (size_t)b * p.Lp + t;
-      uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
-      if (t < p.L) {
-        float v[8];
-        float2 f;
-        f = unpack_h2(yv[i].x); v[0] = f.x; v[1] = f.y;
-        f = unpack_h2(yv[i].y); v[2] = f.x; v[3] = f.y;
-        f = unpack_h2(yv[i].z); v[4] = f.x; v[5] = f.y;
-        f = unpack_h2(yv[i].w); v[6] = f.x; v[7] = f.y;
-        if (MODE == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + te[j]) * m[i];
-        } else {
-          float r[8];
-          f = unpack_h2(rv[i].x); r[0] = f.x; r[1] = f.y;
-          f = unpack_h2(rv[i].y); r[2] = f.x; r[3] = f.y;
-          f = unpack_h2(rv[i].z); r[4] = f.x; r[5] = f.y;
-          f = unpack_h2(rv[i].w); r[6] = f.x; r[7] = f.y;
-          float s = 0.f, ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + r[j];
-            s += v[j];
-            ss = fmaf(v[j], v[j], ss);
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, off);
-            ss += __shfl_xor_sync(0xffffffffu, ss, off);
-          }
-          const float lmean = s * (1.f / 256.f);
-          const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
-          float a[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
-          o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
+        for (int j = 0; j < 8; ++j) {
+          v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + r[j];
+          s += v[j];
+          ss = fmaf(v[j], v[j], ss);
         }
-        o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, off);
+          ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        }
+        const float lmean = s * (1.f / 256.f);
+        const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
+        o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
       }
-      stg128(p.out + row * 256 + c0, o);  // guard rows are written as zeros
-      if (MODE == 1) stg128(p.out2 + row * 256 + c0, o2);
+      o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
     }
+    stg128(p.out + row * 256 + c0, o);  // guard rows are written as zeros
+    if (MODE == 1) stg128(p.out2 + row * 256 + c0, o2);
   }
 }
 

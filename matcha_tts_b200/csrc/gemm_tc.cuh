@@ -91,14 +91,16 @@ struct GemmParams {
   int n_valid;
 };
 
-template <int BN>
+template <int BN, int EPI = EPI_PLAIN>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int PAR_BYTES = 3 * BN * 4;
-  static constexpr int RED_BYTES = GEMM_BM * 2 * 8;  // LayerNorm partial (sum, sumsq) per row and column half
+  // per-column epilogue parameters of ALL n-tiles, staged once per CTA: [bias | p1 | p2] x PAR_N
+  static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : 1024;  // max N of one launch
+  static constexpr int PAR_BYTES = ((EPI == EPI_SNAKE || EPI == EPI_LN) ? 3 : 1) * PAR_N * 4;
+  static constexpr int RED_BYTES = 2 * GEMM_BM * 2 * 8;  // LayerNorm partial (sum, sumsq) per row and column half, x2 buffers
   static constexpr int TOTAL = 1024 /*align slack*/ + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_BYTES +
                                PAR_BYTES + RED_BYTES + 256;
 };
@@ -158,7 +160,8 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using SM = GemmSmem<BN>;
+  using SM = GemmSmem<BN, EPI>;
+  constexpr int PN = SM::PAR_N;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "BN must be 128 or 256");
@@ -194,6 +197,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  // per-column epilogue parameters (weights: independent of the previous kernel) for every n-tile
+  if (warp >= 2) {
+    const int ncols = min(p.n_tiles * BN, PN);
+    for (int i = threadIdx.x - 64; i < ncols; i += 32 * GEMM_EPI_WARPS) {
+      s_par[i] = p.bias ? p.bias[i] : 0.f;
+      if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
+      if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -268,7 +280,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int cbase = hcol * CW;
     const uint32_t st = smem_u32(staging + ew * GEMM_STAGING_BYTES);
     const uint32_t spar = smem_u32(s_par);
-    const int et = threadIdx.x - 64;  // 0..255
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -280,15 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int rows_valid = min(32, p.M - rw0);  // may be <= 0
       const bool row_ok = row < p.M;
 
-      // per-tile column parameters -> smem (all epilogue warps)
-      epi_bar_sync();
-      for (int i = et; i < BN; i += 32 * GEMM_EPI_WARPS) {
-        s_par[i] = p.bias ? p.bias[n0 + i] : 0.f;
-        if constexpr (EPI == EPI_LN) { s_par[BN + i] = p.ln_g[n0 + i]; s_par[2 * BN + i] = p.ln_b[n0 + i]; }
-        if constexpr (EPI == EPI_SNAKE) { s_par[BN + i] = p.sn_a[n0 + i]; s_par[2 * BN + i] = p.sn_ib[n0 + i]; }
-      }
-      epi_bar_sync();
-
+      const uint32_t sp0 = spar + (n0 + cbase) * 4;  // bias of this warp's first column
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + cbase;
 
       if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_LN || EPI == EPI_SNAKE) {
@@ -315,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b4 = lds_f4(spar + (cbase + c * 32 + 4 * j) * 4);
+            const float4 b4 = lds_f4(sp0 + (c * 32 + 4 * j) * 4);
             v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
           if (has_res) {
@@ -325,8 +328,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if constexpr (EPI == EPI_SNAKE) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 a4 = lds_f4(spar + (BN + cbase + c * 32 + 4 * j) * 4);
-              const float4 i4 = lds_f4(spar + (2 * BN + cbase + c * 32 + 4 * j) * 4);
+              const float4 a4 = lds_f4(sp0 + (PN + c * 32 + 4 * j) * 4);
+              const float4 i4 = lds_f4(sp0 + (2 * PN + c * 32 + 4 * j) * 4);
               float s;
               s = fast_sin(v[4 * j + 0] * a4.x); v[4 * j + 0] = fmaf(s * s, i4.x, v[4 * j + 0]);
               s = fast_sin(v[4 * j + 1] * a4.y); v[4 * j + 1] = fmaf(s * s, i4.y, v[4 * j + 1]);
@@ -398,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if constexpr (EPI == EPI_LN) {
           // LayerNorm over the full BN-wide row: combine the two column halves through smem
-          const uint32_t red = smem_u32(s_red);
+          const uint32_t red = smem_u32(s_red) + (as ? GEMM_BM * 16 : 0);  // double-buffered by accumulator stage
           const int trow = q * 32 + lane;
           sts_f32(red + (trow * 2 + hcol) * 8, lsum);
           sts_f32(red + (trow * 2 + hcol) * 8 + 4, lsq);
@@ -420,8 +423,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 g4 = lds_f4(spar + (BN + cbase + c * 32 + 4 * j) * 4);
-              const float4 b4 = lds_f4(spar + (2 * BN + cbase + c * 32 + 4 * j) * 4);
+              const float4 g4 = lds_f4(sp0 + (PN + c * 32 + 4 * j) * 4);
+              const float4 b4 = lds_f4(sp0 + (2 * PN + c * 32 + 4 * j) * 4);
               v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, g4.x, b4.x);
               v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, g4.y, b4.y);
               v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, g4.z, b4.z);
@@ -482,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (b >= 0) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float o = fmaf(p.zscale, (v[j] + lds_f32(spar + (col0 + j) * 4)) * m, zb[j]);
+                const float o = fmaf(p.zscale, (v[j] + lds_f32(sp0 + (c * 32 + j) * 4)) * m, zb[j]);
                 v[j] = o;
               }
 #pragma unroll

@@ -422,7 +422,7 @@ static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 gr
 template <int BN, int EPI>
 static int set_gemm_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN>::TOTAL));
+                                GemmSmem<BN, EPI>::TOTAL));
   return 0;
 }
 
@@ -432,7 +432,7 @@ static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& 
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, stream, a0, a1, wmap, p));
+  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI>::TOTAL, stream, a0, a1, wmap, p));
   launched(h);
   return 0;
 }
@@ -935,7 +935,7 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
 int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
                     int ntaps, const int* shifts, void* stream_) {
   if (!h || !A || !W || !out) return fail(MTTS_EINVAL, "null argument");
-  if (C % 64 || N % 128 || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
+  if (C % 64 || N % 128 || N > 1024 || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
   if (int e = init_encode()) return e;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUtensorMap ma, mw;
