@@ -107,6 +107,15 @@ int mtts_last_launch_count(const MttsHandle* h);
 int mtts_debug_profile_begin(MttsHandle* h, void* stream);
 int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind, double* flops);
 
+/* In-kernel timeline of the GEMM launches (tools/gemm_timeline.py): launch i of the following calls
+ * writes [148 CTAs][16] int64 stamps (clock64 at entry / setup done / dependency wait passed / first
+ * operands landed / last MMA issued / first accumulator ready / epilogue done / exit, and globaltimer
+ * ns at [8] entry, [9] wait passed, [10] exit) at dev_buf + i*148*16.  NULL switches it off. */
+int mtts_debug_set_timeline(MttsHandle* h, void* dev_buf, int max_launches);
+/* Same for the fused transformer-tail kernel: [148 CTAs][128] clock64 stamps of each CTA's first tile
+ * ([0,64) MMA issuer, [64,128) one epilogue warp; see tools/tail_timeline.py); every tail launch overwrites it. */
+int mtts_debug_set_tail_timeline(MttsHandle* h, void* dev_buf);
+
 /* ---- introspection used by the parity tests -------------------------------------------------- */
 /* Stop the estimator after `n` kernel launches (n < 0: run everything). */
 int mtts_debug_set_launch_limit(MttsHandle* h, int n);

@@ -1,0 +1,456 @@
+// Fused "transformer tail" of BasicTransformerBlock (reference model.py:737-744, FeedForward :641-644,
+// SnakeBeta :600-609) for one 128-row tile, everything after the attention product being row-local:
+//
+//   x_a = x_r + o Wo^T + b_o                      (attn1.to_out + residual, :703, :737)
+//   c   = LayerNorm3(x_a)                         (:739)
+//   s   = SnakeBeta(c W1^T + b1)                  (ff.net.0)
+//   out = (x_a + s W2^T + b2) * mask              (ff.net.2 + residual :742; consumers mask the block output)
+//
+// One CTA per SM, persistent over row tiles.  Neither c (128x256) nor s (128x1024) ever leaves the SM:
+//   TMEM  cols [0,256)   R : to_out accumulator -> x_a (fp32, written back by the epilogue) -> FF2 accumulates on top
+//         cols [256,384) D1[2] : double-buffered FF1 accumulator, one 64-wide chunk of the hidden dimension each
+//         cols [384,512) Cc : c = LayerNorm3(x_a) as packed fp16 pairs -- the A operand of FF1 is read from TENSOR
+//                             MEMORY (an N=64 MMA reading a 4 KB A tile from shared memory every 32 cycles would be
+//                             shared-memory-bandwidth bound)
+//   SMEM  S  2x16 KB : s chunk j (128x64 fp16) double-buffered (A operand of FF2)
+//         ring 5x32 KB : TMA-fed operand pieces, ONE cp.async.bulk.tensor each -- an issue costs the thread
+//                        ~330 cycles whatever the box size (profiles/r01_tma_issue_microbench.txt), so pieces
+//                        are as large as a 512-cycle MMA group needs:
+//                          o  tile    box {64, 128 rows, 2 K-chunks} of o  viewed as [2][rows][64]
+//                          Wo K-chunk box {64, 256 rows}                 (B operand, N = 256)
+//                          W1 chunk j box {64, 64 rows, 4 K-chunks}  of W1 viewed as [4][1024][64] (N = 64, K = 256)
+//                          W2 chunk j box {64, 256 rows}                 (B operand, N = 256, K = 64)
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogue (four column groups per TMEM lane
+// quarter = four warps per scheduler: the SnakeBeta epilogue is latency-bound with fewer).  The MMA stream is software-pipelined over the 16 hidden chunks
+//   FF1_0 FF1_1 | FF2_0 FF1_2 | FF2_1 FF1_3 | ... | FF2_14 | FF2_15
+// so that the tensor pipe works on FF2_{j-1} and FF1_{j+1} while the epilogue warps apply SnakeBeta to chunk j.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace mtts {
+
+struct TailParams {
+  int M;                 // rows (flat row space of the level)
+  const __half* xr;      // [rows, 256] resnet output (residual)
+  const float* b_o;      // [256]
+  const float* ln_g;     // [256]
+  const float* ln_b;     // [256]
+  const float* b1;       // [1024]
+  const float* sn_a;     // [1024] exp(alpha)
+  const float* sn_ib;    // [1024] 1/(exp(beta)+1e-9)
+  const float* b2;       // [256]
+  const float* rowmask;  // [rows]
+  __half* out;           // [rows, 256]
+  int w_hint;            // 1: weight pieces are loaded with the L2 evict_last policy
+  long long* tl;         // debug timeline [gridDim.x][128] clock64 stamps of the first tile (null in production)
+};
+
+constexpr int TAIL_NST = 5;
+constexpr int TAIL_PIECE = 32768;
+constexpr int TAIL_NJ = 16;                                           // hidden chunks of 64
+constexpr int TAIL_NCG = 4;                                           // column groups -> 16 epilogue warps (4 per scheduler)
+constexpr int TAIL_THREADS = 64 + 128 * TAIL_NCG;
+constexpr int TAIL_OFF_S = 0;                                         // 2 x 16 KB
+constexpr int TAIL_OFF_RING = TAIL_OFF_S + 2 * 16384;                 // 32768
+constexpr int TAIL_OFF_PAR = TAIL_OFF_RING + TAIL_NST * TAIL_PIECE;   // 196608
+constexpr int TAIL_PAR_FLOATS = 4 * 256 + 3 * 1024;                   // b_o ln_g ln_b b2 | b1 sn_a sn_ib
+// epilogue staging (16 warps x 32 rows x 64 B = 32 KB) aliases the S buffers: it is only used at the start (E1)
+// and at the end (E3) of a tile, when no FF2 MMA can be reading S (r_full / r_done imply all MMAs retired)
+constexpr int TAIL_OFF_STAGING = TAIL_OFF_S;
+constexpr int TAIL_OFF_RED = TAIL_OFF_PAR + TAIL_PAR_FLOATS * 4;      // 212992: LayerNorm partials [128][NCG] float2
+constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;       // 217088
+constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;                         // 217344
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
+ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmWo,
+               const __grid_constant__ CUtensorMap tmW1_3, const __grid_constant__ CUtensorMap tmW2, const TailParams p) {
+  constexpr int NCG = TAIL_NCG;
+  constexpr int NEW = 4 * NCG;       // epilogue warps
+  constexpr int CW1 = 256 / NCG;     // columns per warp in the 256-wide phases
+  constexpr int NCH1 = CW1 / 32;
+  constexpr int CW2 = 64 / NCG;      // columns per warp in a 64-wide FF1 chunk (= 16: one TMEM load)
+  static_assert(CW2 == 16, "one 16-column TMEM load per thread and hidden chunk");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float* s_par = reinterpret_cast<float*>(smem + TAIL_OFF_PAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TAIL_OFF_BAR);
+  uint64_t* full_bar = bars;                        // [TAIL_NST]
+  uint64_t* empty_bar = bars + TAIL_NST;            // [TAIL_NST]
+  uint64_t* r_full = bars + 2 * TAIL_NST;           // to_out accumulator complete
+  uint64_t* c_ready = r_full + 1;                   // c written to TMEM, x_a written back to TMEM
+  uint64_t* d1_full = r_full + 2;                   // [2] FF1 chunk accumulator complete
+  uint64_t* d1_empty = r_full + 4;                  // [2] epilogue has read the FF1 chunk accumulator
+  uint64_t* s_ready = r_full + 6;                   // [2] s chunk written to smem
+  uint64_t* s_empty = r_full + 8;                   // [2] FF2 has consumed the s chunk
+  uint64_t* r_done = r_full + 10;                   // all FF2 MMAs of the tile complete
+  uint64_t* r_empty = r_full + 11;                  // epilogue has read the final accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 12);
+  static_assert((2 * TAIL_NST + 13) * 8 <= 256, "barrier block");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int m_tiles = (p.M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TAIL_NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(r_full, 1); mbar_init(c_ready, NEW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NEW);
+      mbar_init(&s_ready[i], NEW); mbar_init(&s_empty[i], 1);
+    }
+    mbar_init(r_done, 1); mbar_init(r_empty, NEW);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmO3); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1_3); tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp >= 2) {  // weights-only parameters: staged while the previous kernel drains
+    for (int i = threadIdx.x - 64; i < 256; i += 32 * NEW) {
+      s_par[i] = p.b_o[i]; s_par[256 + i] = p.ln_g[i]; s_par[512 + i] = p.ln_b[i]; s_par[768 + i] = p.b2[i];
+    }
+    for (int i = threadIdx.x - 64; i < 1024; i += 32 * NEW) {
+      s_par[1024 + i] = p.b1[i]; s_par[2048 + i] = p.sn_a[i]; s_par[3072 + i] = p.sn_ib[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tR = tmem_base;
+  const uint32_t tD1 = tmem_base + 256;
+  const uint32_t tC = tmem_base + 384;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    // converged warp, one elected lane per instruction (keeps descriptors/coordinates in uniform registers)
+    if ((int)blockIdx.x < m_tiles) {
+      uint32_t it = 0;  // running ring item counter
+      const uint64_t pol = l2_policy_evict_last();
+      auto slot_acquire = [&]() -> uint32_t {
+        const uint32_t slot = it % TAIL_NST, use = it / TAIL_NST;
+        mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
+        ++it;
+        return slot;
+      };
+      auto put2 = [&](const CUtensorMap* tm, int c0, int c1) {  // weights: [256 rows x 64 cols]
+        const uint32_t slot = slot_acquire();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
+          if (p.w_hint) tma_load_2d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, tm, &full_bar[slot], c0, c1, pol);
+          else tma_load_2d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, tm, &full_bar[slot], c0, c1);
+        }
+        __syncwarp();
+      };
+      auto put_w1 = [&](int j) {
+        const uint32_t slot = slot_acquire();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
+          if (p.w_hint) tma_load_3d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 64, 0, pol);
+          else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 64, 0);
+        }
+        __syncwarp();
+      };
+      bool first = true;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        put2(&tmWo, 0, 0);   // Wo K-chunk 0
+        put2(&tmWo, 64, 0);  // Wo K-chunk 1
+        if (first) { pdl_wait(); first = false; }  // o is the first operand produced by the previous kernel
+        {
+          const uint32_t slot = slot_acquire();
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
+            tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, &full_bar[slot], 0, tile * 128, 0);
+          }
+          __syncwarp();
+        }
+        put_w1(0);
+        for (int j = 0; j < TAIL_NJ; ++j) {
+          if (j + 1 < TAIL_NJ) put_w1(j + 1);
+          put2(&tmW2, j * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    // The whole warp runs this code converged (addresses and descriptors stay in uniform registers);
+    // only the tcgen05 instructions themselves are issued by one elected lane.
+    {
+      constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
+      constexpr uint32_t idesc64 = umma_idesc_f16(128, 64);
+      const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
+      const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
+      uint32_t it = 0;  // ring item counter (same sequence as the producer)
+      uint32_t n_tile = 0, n_d1e0 = 0, n_d1e1 = 0, n_sr0 = 0, n_sr1 = 0;
+      auto slot_wait = [&](uint32_t item) -> uint32_t {
+        const uint32_t slot = item % TAIL_NST, use = item / TAIL_NST;
+        mbar_wait(&full_bar[slot], use & 1);
+        tc_fence_after();
+        return ring + slot * TAIL_PIECE;
+      };
+      long long* tl = (p.tl != nullptr) ? p.tl + (size_t)blockIdx.x * 128 : nullptr;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+        if (n_tile != 0) tl = nullptr;
+        // ---- to_out: R = o Wo^T ; ring items: base+0, base+1 = Wo K-chunks, base+2 = o (both K-chunks)
+        mbar_wait(r_empty, (n_tile & 1) ^ 1);
+        tc_fence_after();
+        if (tl && lane == 0) tl[0] = clock64();
+        const uint32_t base = it;
+        {
+          const uint32_t a = slot_wait(base + 2);
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t b = slot_wait(base + k);
+            const uint64_t da = umma_desc_sw128(a + k * 16384), db = umma_desc_sw128(b);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, (k | kk) != 0);
+              umma_commit(&empty_bar[(base + k) % TAIL_NST]);
+              if (k == 1) { umma_commit(&empty_bar[(base + 2) % TAIL_NST]); umma_commit(r_full); }
+            }
+            __syncwarp();
+          }
+        }
+        if (tl && lane == 0) tl[1] = clock64();
+        it = base + 3;
+        // ---- feed-forward
+        mbar_wait(c_ready, n_tile & 1);
+        tc_fence_after();
+        if (tl && lane == 0) tl[2] = clock64();
+        auto ff1 = [&](int j) {
+          const int b = j & 1;
+          uint32_t& n = b ? n_d1e1 : n_d1e0;
+          mbar_wait(&d1_empty[b], (n & 1) ^ 1);
+          ++n;
+          tc_fence_after();
+          if (tl && lane == 0 && j < 8) tl[4 + 4 * j] = clock64();
+          const uint32_t w = slot_wait(it);
+          const uint64_t db0 = umma_desc_sw128(w);
+          if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B descriptor address in 16-byte units
+#ifdef TAIL_DEBUG_NO_TS
+                umma_f16(tD1 + b * 64, db0 + 2 * kk, db0 + kc * (8192 >> 4) + 2 * kk, idesc64, (kc | kk) != 0);
+#else
+                umma_f16_ts(tD1 + b * 64, tC + kc * 32 + kk * 8, db0 + kc * (8192 >> 4) + 2 * kk, idesc64, (kc | kk) != 0);
+#endif
+            umma_commit(&empty_bar[it % TAIL_NST]);
+            umma_commit(&d1_full[b]);
+          }
+          __syncwarp();
+          ++it;
+          if (tl && lane == 0 && j < 8) tl[5 + 4 * j] = clock64();
+        };
+        auto ff2 = [&](int j) {
+          const int b = j & 1;
+          uint32_t& n = b ? n_sr1 : n_sr0;
+          mbar_wait(&s_ready[b], n & 1);
+          ++n;
+          tc_fence_after();
+          if (tl && lane == 0 && j < 8) tl[6 + 4 * j] = clock64();
+          const uint32_t w = slot_wait(it);
+          const uint64_t da = umma_desc_sw128(sbuf + b * 16384), db = umma_desc_sw128(w);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
+            umma_commit(&empty_bar[it % TAIL_NST]);
+            umma_commit(&s_empty[b]);
+          }
+          __syncwarp();
+          ++it;
+          if (tl && lane == 0 && j < 8) tl[7 + 4 * j] = clock64();
+        };
+        ff1(0);
+        for (int j = 0; j < TAIL_NJ; ++j) {
+          if (j + 1 < TAIL_NJ) ff1(j + 1);
+          ff2(j);
+        }
+        if (elect_one()) umma_commit(r_done);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int ew = warp - 2;
+    const int q = warp & 3;     // TMEM lane quarter
+    const int cg = ew >> 2;     // column group
+    const uint32_t st = smem_u32(smem + TAIL_OFF_STAGING + ew * GEMM_STAGING_BYTES);
+    const uint32_t spar = smem_u32(s_par);
+    const uint32_t red = smem_u32(smem + TAIL_OFF_RED);
+    const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const int trow = q * 32 + lane;  // row inside the tile
+    uint32_t n_tile = 0, n_d1f[2] = {0, 0}, n_se[2] = {0, 0};
+    long long* tl = (p.tl != nullptr && ew == 0 && lane == 0) ? p.tl + (size_t)blockIdx.x * 128 + 64 : nullptr;
+    pdl_wait();  // x_r / out belong to the dependency chain
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+      if (n_tile != 0) tl = nullptr;
+      const int rw0 = tile * 128 + q * 32;
+      const int row = rw0 + lane;
+      const int rows_valid = min(32, p.M - rw0);
+      // ------------------------------------------------ E1: x_a, LayerNorm3 -> c
+      {
+        const __half* rbase = p.xr + (size_t)rw0 * 256 + cg * CW1;
+        uint4 rr[4];
+        epi_resid_issue(rr, lane, rbase, 256, rows_valid);
+        if (lane == 0) mbar_wait(r_full, n_tile & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (tl) tl[0] = clock64();
+        const uint32_t ta = tR + lane_off + cg * CW1;
+        float lsum = 0.f, lsq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH1; ++c) {
+          float v[32];
+          tmem_ld32(ta + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = lds_f4(spar + (cg * CW1 + c * 32 + 4 * j) * 4);
+            v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+          epi_resid_add(st, lane, rr, v);
+          __syncwarp();
+          if (c + 1 < NCH1) epi_resid_issue(rr, lane, rbase + (c + 1) * 32, 256, rows_valid);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { lsum += v[j]; lsq = fmaf(v[j], v[j], lsq); }
+          tmem_st32(ta + c * 32, v);
+        }
+        sts_f32(red + (trow * NCG + cg) * 8, lsum);
+        sts_f32(red + (trow * NCG + cg) * 8 + 4, lsq);
+        tmem_st_wait();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
+        float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+        for (int g = 0; g < NCG; ++g) {  // fixed order: every warp of a row sees identical statistics
+          tsum += lds_f32(red + (trow * NCG + g) * 8);
+          tsq += lds_f32(red + (trow * NCG + g) * 8 + 4);
+        }
+        const float mean = tsum * (1.f / 256.f);
+        const float rstd = rsqrtf(fmaxf(tsq * (1.f / 256.f) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+        for (int c = 0; c < NCH1; ++c) {
+          float v[32];
+          tmem_ld32(ta + c * 32, v);
+          tmem_ld_wait();
+          const int col = cg * CW1 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = lds_f4(spar + (256 + col + 4 * j) * 4);
+            const float4 b4 = lds_f4(spar + (512 + col + 4 * j) * 4);
+            v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, g4.x, b4.x);
+            v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, g4.y, b4.y);
+            v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, g4.z, b4.z);
+            v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, g4.w, b4.w);
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) pk[u] = pack_h2(v[2 * u], v[2 * u + 1]);
+          tmem_st16(tC + lane_off + (col >> 1), pk);  // c as fp16 pairs: A operand of FF1, read from TMEM
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c_ready);
+        if (tl) tl[1] = clock64();
+      }
+      // ------------------------------------------------ E2: SnakeBeta on the 16 hidden chunks
+#pragma unroll 1
+      for (int j = 0; j < TAIL_NJ; ++j) {
+        const int b = j & 1;
+        if (lane == 0) {
+          mbar_wait(&s_empty[b], (n_se[b] & 1) ^ 1);  // FF2_{j-2} no longer reads S[b]
+          mbar_wait(&d1_full[b], n_d1f[b] & 1);
+        }
+        ++n_se[b];
+        ++n_d1f[b];
+        __syncwarp();
+        tc_fence_after();
+        if (tl && j < 8) tl[4 + 2 * j] = clock64();
+        float v[16];
+        tmem_ld16(tD1 + b * 64 + lane_off + cg * 16, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d1_empty[b]);  // the accumulator chunk is in registers: FF1_{j+2} may overwrite it
+        const uint32_t pb = spar + (1024 + j * 64 + cg * 16) * 4;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 b4 = lds_f4(pb + jj * 16);
+          const float4 a4 = lds_f4(pb + 4096 + jj * 16);
+          const float4 i4 = lds_f4(pb + 8192 + jj * 16);
+          float x, sn;
+          x = v[4 * jj + 0] + b4.x; sn = fast_sin(x * a4.x); v[4 * jj + 0] = fmaf(sn * sn, i4.x, x);
+          x = v[4 * jj + 1] + b4.y; sn = fast_sin(x * a4.y); v[4 * jj + 1] = fmaf(sn * sn, i4.y, x);
+          x = v[4 * jj + 2] + b4.z; sn = fast_sin(x * a4.z); v[4 * jj + 2] = fmaf(sn * sn, i4.z, x);
+          x = v[4 * jj + 3] + b4.w; sn = fast_sin(x * a4.w); v[4 * jj + 3] = fmaf(sn * sn, i4.w, x);
+        }
+        const uint32_t srow = sbuf + b * 16384 + trow * 128;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          sts128(srow + (((cg * 2 + u) ^ (trow & 7)) << 4),
+                 make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                            pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_ready[b]);
+        if (tl && j < 8) tl[5 + 2 * j] = clock64();
+      }
+      // ------------------------------------------------ E3: out = (x_a + FF + b2) * mask
+      {
+        float mrow = 0.f;
+        if (row < p.M) mrow = p.rowmask[row];
+        if (lane == 0) mbar_wait(r_done, n_tile & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (tl) tl[2] = clock64();
+        const uint32_t ta = tR + lane_off + cg * CW1;
+        __half* obase = p.out + (size_t)rw0 * 256 + cg * CW1;
+        float vbuf[2][32];
+        tmem_ld32(ta, vbuf[0]);
+#pragma unroll
+        for (int c = 0; c < NCH1; ++c) {
+          float* v = vbuf[c & 1];
+          tmem_ld_wait();
+          if (c + 1 < NCH1) tmem_ld32(ta + (c + 1) * 32, vbuf[(c + 1) & 1]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = lds_f4(spar + (768 + cg * CW1 + c * 32 + 4 * j) * 4);
+            v[4 * j + 0] = (mrow == 0.f) ? 0.f : (v[4 * j + 0] + b4.x) * mrow;
+            v[4 * j + 1] = (mrow == 0.f) ? 0.f : (v[4 * j + 1] + b4.y) * mrow;
+            v[4 * j + 2] = (mrow == 0.f) ? 0.f : (v[4 * j + 2] + b4.z) * mrow;
+            v[4 * j + 3] = (mrow == 0.f) ? 0.f : (v[4 * j + 3] + b4.w) * mrow;
+          }
+          epi_store_h32(st, lane, v, obase + c * 32, 256, rows_valid);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r_empty);
+        if (tl) tl[3] = clock64();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace mtts

@@ -9,10 +9,14 @@
 // `torch.cat` along channels is a second tensor map in the K loop.  Weights are pre-packed
 // [N, Ktot] K-major fp16.  Accumulation is fp32 in TMEM.
 //
-// Warp roles (320 threads, persistent over tiles, 1 CTA / SM):
-//   warp 0   TMA producer   (A tile 128x64 + B tile BNx64 per stage, 128B swizzle, mbarrier tx)
+// Warp roles (352 threads, persistent over tiles, 1 CTA / SM):
+//   warp 0   TMA producer of the activation (A) tiles, 128x64 per stage (128B swizzle, mbarrier tx)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (4 x K16 per stage), tcgen05.commit
-//   warps 2-9 epilogue: two warps per TMEM lane quarter, each owning half of the tile's columns;
+//   warp 2   TMA producer of the weight (B) tiles, BNx64 per stage.  A cp.async.bulk.tensor costs its
+//            issuing thread ~330 cycles whatever the box size (profiles/r01_tma_issue_microbench.txt), so
+//            one thread issuing both tiles would cap a 512-cycle stage; the weight producer also never
+//            waits for the previous kernel (weights are constants), so its first tiles land during PDL overlap.
+//   warps 3-10 epilogue: two warps per TMEM lane quarter, each owning half of the tile's columns;
 //             tcgen05.ld (one accumulator row per thread, 32 columns at a time), fused math,
 //             swizzled smem staging -> 64-byte-per-row coalesced global stores; residual tiles are
 //             prefetched into registers one chunk ahead.  Two accumulator stages in TMEM overlap
@@ -38,7 +42,7 @@ namespace mtts {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;        // 320
+constexpr int GEMM_THREADS = 96 + 32 * GEMM_EPI_WARPS;        // 352: A producer, MMA, B producer, 8 epilogue warps
 constexpr int GEMM_MAX_SEGS = 9;
 constexpr int GEMM_STAGING_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 32 fp16, swizzled
 
@@ -89,6 +93,9 @@ struct GemmParams {
   int ldx0;
   int T;
   int n_valid;
+  // debug: per-CTA timeline [gridDim.x][16] (clock64 / globaltimer stamps), null in production
+  long long* tl;
+  int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
 };
 
 template <int BN, int EPI = EPI_PLAIN>
@@ -182,6 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();  // the next kernel may start its prologue; it still waits for our completion
+  long long* tl = p.tl ? p.tl + (size_t)blockIdx.x * 16 : nullptr;
+  if (tl && threadIdx.x == 0) { tl[0] = clock64(); tl[8] = (long long)globaltimer_ns(); }
 
   int total_chunks = 0;
   for (int s = 0; s < p.num_segs; ++s) total_chunks += p.seg[s].nchunks;
@@ -189,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int total_tiles = m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
@@ -198,9 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   // per-column epilogue parameters (weights: independent of the previous kernel) for every n-tile
-  if (warp >= 2) {
+  if (warp >= 3) {
     const int ncols = min(p.n_tiles * BN, PN);
-    for (int i = threadIdx.x - 64; i < ncols; i += 32 * GEMM_EPI_WARPS) {
+    for (int i = threadIdx.x - 96; i < ncols; i += 32 * GEMM_EPI_WARPS) {
       s_par[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
       if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
@@ -210,27 +219,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && threadIdx.x == 0) tl[1] = clock64();
+
+  if (warp == 2) {
+    // ===================================== TMA producer: weights (no dependency wait) ==========
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint64_t pol = l2_policy_evict_last();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_tiles) * BN;
+      for (int kc = 0; kc < total_chunks; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);   // converged warp; one elected lane issues
+        if (elect_one()) {
+          uint8_t* sb = smem + stage * SM::STAGE_BYTES + SM::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], SM::B_BYTES);
+          if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
+          else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
 
   pdl_wait();  // everything below touches memory the previous kernel may still be using
+  if (tl && threadIdx.x == 0) { tl[2] = clock64(); tl[9] = (long long)globaltimer_ns(); }
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer: activations ===========================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int r0 = (tile / p.n_tiles) * GEMM_BM;
-      const int n0 = (tile % p.n_tiles) * BN;
-      int kc = 0;
       for (int s = 0; s < p.num_segs; ++s) {
         const GemmSeg sg = p.seg[s];
         const CUtensorMap* tm = sg.src ? &tmA1 : &tmA0;
-        for (int c = 0; c < sg.nchunks; ++c, ++kc) {
-          if (lane == 0) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * SM::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-            tma_load_2d(sa, tm, &full_bar[stage], sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
-            tma_load_2d(sa + SM::A_BYTES, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+        for (int c = 0; c < sg.nchunks; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], SM::A_BYTES);
+            tma_load_2d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -245,36 +273,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      if (lane == 0) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+      // converged warp: waits by every lane, tcgen05 instructions by one elected lane (uniform operands)
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kc = 0; kc < total_chunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        if (tl && lane == 0 && kc == 0 && tile == (int)blockIdx.x) tl[3] = clock64();
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kc = 0; kc < total_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + SM::A_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+        const uint64_t da = umma_desc_sw128(sa);
+        const uint64_t db = umma_desc_sw128(sa + SM::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kc == total_chunks - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&tfull_bar[as]);
-      } else {
-        for (int kc = 0; kc < total_chunks; ++kc)
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
+      if (tl && lane == 0) tl[4] = clock64();
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-  } else {
+  } else if (warp >= 3) {
     // ===================================== epilogue =========================================
     constexpr int CW = BN / 2;    // columns per epilogue warp
     constexpr int NCH = CW / 32;  // 32-column chunks per warp
-    const int ew = warp - 2;
+    const int ew = warp - 3;
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int hcol = ew >> 2;     // which half of the tile's columns
     const int cbase = hcol * CW;
@@ -307,15 +335,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
+        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
 
         float gs[(EPI == EPI_STATS) ? 2 * NCH : 1];
         float lsum = 0.f, lsq = 0.f;
         __half* obase = p.out + (size_t)rw0 * p.ldo + n0 + cbase;
+        float vbuf[2][32];  // accumulator chunk c+1 is fetched from TMEM while chunk c is processed
+        tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
+          float* v = vbuf[c & 1];
           tmem_ld_wait();
+          if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = lds_f4(sp0 + (c * 32 + 4 * j) * 4);
@@ -350,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if constexpr (EPI == EPI_PLAIN) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= mrow;
+            for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }
           epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
         }
@@ -437,6 +468,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
+        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
         if (n_tile < 2) {
           __half* dst = (n_tile == 0 ? p.q : p.k) + (size_t)rw0 * BN + cbase;
 #pragma unroll
@@ -470,6 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
+        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int col0 = cbase + c * 32;
@@ -504,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
 
+      if (tl && ew == 0 && lane == 0) tl[6] = clock64();
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -516,6 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (tl && threadIdx.x == 0) { tl[7] = clock64(); tl[10] = (long long)globaltimer_ns(); }
 }
 
 }  // namespace mtts

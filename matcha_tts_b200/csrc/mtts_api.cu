@@ -16,6 +16,7 @@
 #include "../../include/mtts.h"
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "ff_tail.cuh"
 #include "gemm_tc.cuh"
 
 using namespace mtts;
@@ -70,6 +71,25 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return 0;
 }
 
+// fp16 [rows, nk*64] row-major viewed as [nk][rows][64]: one box = nk K-chunks of box_rows x 64, landing in
+// shared memory as nk consecutive 128B-swizzled tiles (a single TMA instruction for a whole operand piece)
+static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t nk, uint64_t pitch, uint32_t box_rows) {
+  cuuint64_t dims[3] = {64, rows, nk};
+  cuuint64_t strides[2] = {pitch * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, nk};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(3d) failed (%d) rows=%llu nk=%u pitch=%llu box_rows=%u", (int)r,
+             (unsigned long long)rows, nk, (unsigned long long)pitch, box_rows);
+    return fail(MTTS_ECUDA, buf);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
@@ -97,6 +117,7 @@ struct StageW {
   size_t c1, c2, res, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets)
   size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
   CUtensorMap m_c1, m_c2, m_res, m_qkv, m_wo, m_ff1, m_ff2;
+  CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 64, 4}: one hidden chunk of the fused tail (ff_tail.cuh)
 };
 
 struct WsLayout {
@@ -109,6 +130,7 @@ struct WsLayout {
 
 struct LevelMaps {
   CUtensorMap h1, a, o, s, q, k, vt;
+  CUtensorMap o3;  // o as [2][rows][64], box {64, 128, 2} (fused tail)
 };
 struct Plan {
   WsLayout w;
@@ -143,13 +165,25 @@ struct MttsHandle {
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
   int launch_count = 0, launch_limit = -1;
+  bool w_hint = true;      // MTTS_NO_WHINT=1: load weights without the L2 evict_last hint
+  bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
+  // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
+  // every kernel of a chain is small (tens of tiles) and latency-bound on its own
+  int nsub_override = 0;  // MTTS_NSUB in the environment; 0 = heuristic
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> ev_join;
+  cudaEvent_t ev_fork = nullptr;
   // optional per-launch device timing (CUDA events on the launching stream)
   bool profiling = false;
   cudaStream_t prof_stream = nullptr;
   std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
   std::vector<int> prof_kind;            // MTTS_KIND_*
   std::vector<double> prof_flops;        // algorithmic FLOPs of the launch
+  // optional in-kernel timeline of the GEMM launches (debug): [max_launches][148][16] int64
+  long long* tl_buf = nullptr;
+  long long* tail_tl = nullptr;  // ff_tail_kernel timeline (last launch wins), [148][128] int64
+  int tl_max = 0, tl_count = 0;
 };
 
 static const char* kStageNames[6] = {"down_blocks.0", "down_blocks.1", "mid_blocks.0",
@@ -285,6 +319,7 @@ static int build_weight_maps(MttsHandle* h) {
     if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff2, a + w.ff2, C, 4 * C, 4 * C, 256)) return MTTS_ECUDA;
+    if (make_map3(&w.t_ff1, a + w.ff1, 4 * C, 4, C, 64)) return MTTS_ECUDA;
   }
   if (make_map(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
   if (make_map(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
@@ -354,6 +389,7 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
     if (make_map(&m.h1, b + w.h1, rows, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&m.a, b + w.a, rows, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&m.o, b + w.o, rows, 128, 128, 128)) return MTTS_ECUDA;
+    if (make_map3(&m.o3, b + w.o, rows, 2, 128, 128)) return MTTS_ECUDA;
     if (make_map(&m.s, b + w.s, rows, 4 * C, 4 * C, 128)) return MTTS_ECUDA;
     if (make_map(&m.q, b + w.q, rows, 128, 128, 128)) return MTTS_ECUDA;
     if (make_map(&m.k, b + w.k, rows, 128, 128, 128)) return MTTS_ECUDA;
@@ -432,7 +468,11 @@ static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& 
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI>::TOTAL, stream, a0, a1, wmap, p));
+  GemmParams pp = p;
+  pp.tl = nullptr;
+  pp.w_hint = h->w_hint ? 1 : 0;
+  if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
+  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI>::TOTAL, stream, a0, a1, wmap, pp));
   launched(h);
   return 0;
 }
@@ -527,6 +567,21 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     dim3 grid((lc.L + 127) / 128, 2, w.B);
     CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
     launched(h);
+  }
+  if (h->fused_tail) {
+    // x_a = x_r + o Wo^T + b_o ; c = LN3(x_a) ; out = (x_a + SnakeBeta(c W1^T + b1) W2^T + b2) * m   -- one kernel
+    if (can_launch(h, MTTS_KIND_GEMM, fr * C * 128 + 2.0 * fr * 4 * C * C)) {
+      TailParams tp{};
+      tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
+      tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
+      tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0;
+      tp.tl = h->tail_tl;
+      const int tiles = (lc.rows + 127) / 128;
+      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+      CUDA_TRY(launch_k(h, ff_tail_kernel, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
+      launched(h);
+    }
+    return 0;
   }
   // x_a = x_r + o Wo^T + b ; c = LN3(x_a)
   {
@@ -681,6 +736,58 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
 }
 
 // ------------------------------------------------------------------------------------------------
+// utterance chains: a solve of B utterances is split into nsub independent sub-batches
+// ------------------------------------------------------------------------------------------------
+struct Chunk { int b0, nb; size_t ws_off; };
+
+static int pick_nsub(const MttsHandle* h, int B, int T) {
+  int n = h->nsub_override;
+  if (n <= 0) {
+    // aim at >= ~20 row tiles of 128 per chain at level T, at most 8 chains
+    const long rows = (long)B * (T + 2);
+    n = (int)(rows / 2560);
+  }
+  if (n > 8) n = 8;
+  if (n > B) n = B;
+  if (n < 1) n = 1;
+  return n;
+}
+
+// Workspace = [single-call estimator layout for (B, T)] [chain 0 layout] [chain 1 layout] ...
+// The regions are disjoint: each plan zero-fills its region once and relies on its guard rows
+// staying zero afterwards.
+static bool make_chunks(const MttsHandle* h, int B, int T, int nsub, std::vector<Chunk>* out, size_t* total) {
+  out->clear();
+  WsLayout full;
+  if (!ws_layout(h, B, T, &full)) return false;
+  size_t off = align_up(full.total, 1024);
+  int b0 = 0;
+  for (int i = 0; i < nsub; ++i) {
+    const int nb = B / nsub + (i < B % nsub ? 1 : 0);
+    WsLayout w;
+    if (!ws_layout(h, nb, T, &w)) return false;
+    out->push_back(Chunk{b0, nb, off});
+    off += align_up(w.total, 1024);
+    b0 += nb;
+  }
+  *total = off;
+  return true;
+}
+
+static int ensure_side_streams(MttsHandle* h, int nsub) {
+  if (!h->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  while ((int)h->side.size() < nsub - 1) {
+    cudaStream_t st;
+    cudaEvent_t ev;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->side.push_back(st);
+    h->ev_join.push_back(ev);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -703,6 +810,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
+  if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
@@ -722,6 +832,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV>(); e |= set_gemm_attr<128, EPI_FINAL>();
     e |= set_gemm_attr<128, EPI_PLAIN>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
   } else {
     cudaGetLastError();  // no GPU: tables/sizes still work (used by the CPU-side tests); compute calls will fail
@@ -733,6 +844,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
 void mtts_destroy(MttsHandle* h) {
   if (!h) return;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+  for (cudaStream_t st : h->side) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -791,7 +905,12 @@ int mtts_weights_loaded(const MttsHandle* h) {
 size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T) {
   WsLayout w;
   if (!h || !ws_layout(h, B, T, &w)) return 0;
-  return w.total;
+  // the single-call estimator uses one layout for the whole batch; the solver splits the batch into
+  // chains, each with its own (smaller) layout placed after it
+  std::vector<Chunk> ch;
+  size_t total = 0;
+  if (!make_chunks(h, B, T, pick_nsub(h, B, T), &ch, &total)) return 0;
+  return total;
 }
 
 static int check_ready(MttsHandle* h) {
@@ -844,6 +963,30 @@ static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, cons
   return 0;
 }
 
+// all chains of one solve: chain 0 on `stream`, the others on forked side streams, joined at the end
+static int enqueue_solve_chains(MttsHandle* h, const std::vector<Chunk>& chunks, std::vector<Plan*>& plans, float* z,
+                                const float* mu, const float* mask, const float* spks, int n, int solver, int T,
+                                cudaStream_t stream) {
+  const int nsub = (int)chunks.size();
+  const size_t NF = h->cfg.out_channels;
+  if (nsub > 1) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
+    for (int i = 1; i < nsub; ++i) CUDA_TRY(cudaStreamWaitEvent(h->side[i - 1], h->ev_fork, 0));
+  }
+  for (int i = 0; i < nsub; ++i) {
+    const Chunk& c = chunks[i];
+    cudaStream_t st = i == 0 ? stream : h->side[i - 1];
+    if (int e = enqueue_solve(h, *plans[i], z + (size_t)c.b0 * NF * T, mu + (size_t)c.b0 * NF * T, mask + (size_t)c.b0 * T,
+                              spks ? spks + (size_t)c.b0 * h->nspk : nullptr, n, solver, st))
+      return e;
+  }
+  for (int i = 1; i < nsub; ++i) {
+    CUDA_TRY(cudaEventRecord(h->ev_join[i - 1], h->side[i - 1]));
+    CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i - 1], 0));
+  }
+  return 0;
+}
+
 int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask, const float* spks, int n, int solver,
                      void* workspace, size_t workspace_bytes, int B, int T, int use_graph, void* stream_) {
   if (int e = check_ready(h)) return e;
@@ -853,17 +996,27 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
   if (n < 1 || 2 * n > kMaxTimes) return fail(MTTS_EINVAL, "n_timesteps out of range [1, 1024]");
   if (solver != MTTS_SOLVER_EULER && solver != MTTS_SOLVER_MIDPOINT) return fail(MTTS_EINVAL, "unknown solver");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  Plan* P;
-  if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
+  const bool debug_mode = h->launch_limit >= 0 || h->profiling;   // per-launch introspection: one chain
+  const int nsub = debug_mode ? 1 : pick_nsub(h, B, T);
+  std::vector<Chunk> chunks;
+  size_t need = 0;
+  if (!make_chunks(h, B, T, nsub, &chunks, &need)) return fail(MTTS_EINVAL, "unsupported shape: need B >= 1, T even and >= 2");
+  if (workspace_bytes < need) return fail(MTTS_ENOMEM, "workspace too small (see mtts_workspace_bytes)");
+  if (int e = ensure_side_streams(h, nsub)) return e;
+  std::vector<Plan*> plans(nsub);
+  for (int i = 0; i < nsub; ++i) {
+    const size_t avail = (i + 1 < nsub ? chunks[i + 1].ws_off : need) - chunks[i].ws_off;
+    if (int e = get_plan(h, static_cast<char*>(workspace) + chunks[i].ws_off, avail, chunks[i].nb, T, stream, &plans[i])) return e;
+  }
   h->launch_count = 0;
-  if (!use_graph || h->launch_limit >= 0 || h->profiling) return enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
+  if (!use_graph || debug_mode) return enqueue_solve_chains(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
 
   GraphKey key{z, mu, mask, spks, workspace, B, T, n, solver};
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    int e = enqueue_solve(h, *P, z, mu, mask, spks, n, solver, stream);
+    int e = enqueue_solve_chains(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
     cudaError_t ce = cudaStreamEndCapture(stream, &graph);
     if (e) { if (graph) cudaGraphDestroy(graph); return e; }
     if (ce != cudaSuccess) return fail(MTTS_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
@@ -908,6 +1061,20 @@ int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind,
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->prof_events.clear(); h->prof_kind.clear(); h->prof_flops.clear();
   return n;
+}
+
+int mtts_debug_set_timeline(MttsHandle* h, void* dev_buf, int max_launches) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  h->tl_buf = static_cast<long long*>(dev_buf);
+  h->tl_max = dev_buf ? max_launches : 0;
+  h->tl_count = 0;
+  return 0;
+}
+
+int mtts_debug_set_tail_timeline(MttsHandle* h, void* dev_buf) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  h->tail_tl = static_cast<long long*>(dev_buf);
+  return 0;
 }
 
 int mtts_debug_set_launch_limit(MttsHandle* h, int n) {
