@@ -25,7 +25,8 @@
 // prefetch) runs while the previous kernel drains; griddepcontrol.wait precedes the first global access.
 //
 // Fused epilogues (reference file:line each one replaces is listed in DESIGN.md):
-//   EPI_STATS  +bias, fp16 store, deterministic GroupNorm partial sums per (utterance, group)
+//   EPI_STATS  +bias, fp16 store, deterministic GroupNorm partial sums per (utterance, group); optionally a
+//              second accumulator fed by extra K chunks of the same A tiles (the ResnetBlock1D 1x1 res_conv)
 //   EPI_PLAIN  +bias (+residual) (*row mask), fp16 store
 //   EPI_LN     +bias +residual -> fp16 store, then LayerNorm(256) of the same row -> second fp16 store
 //   EPI_SNAKE  +bias, SnakeBeta, fp16 store
@@ -73,6 +74,11 @@ struct GemmParams {
   // EPI_STATS
   float* stats_part;  // [B][S][16]
   int S;
+  // EPI_STATS, optional second GEMM sharing the A tiles (ResnetBlock1D.res_conv next to block1's conv):
+  // K chunks [res_chunk0, total) accumulate into a second TMEM accumulator -> res_out = acc1 + res_bias
+  int res_chunk0;       // 0 = no second GEMM
+  const float* res_bias;
+  __half* res_out;      // [row*ldo + n]
   // EPI_LN
   const float* ln_g;
   const float* ln_b;
@@ -213,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       s_par[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
       if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
+      if constexpr (EPI == EPI_STATS) if (p.res_chunk0 > 0 && i < BN) s_par[512 + i] = p.res_bias[i];
     }
   }
   tc_fence_before();
@@ -276,8 +283,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // converged warp: waits by every lane, tcgen05 instructions by one elected lane (uniform operands)
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      const int rc0 = (EPI == EPI_STATS && p.res_chunk0 > 0) ? p.res_chunk0 : total_chunks;  // dual: both TMEM halves
       for (int kc = 0; kc < total_chunks; ++kc) {
+        const uint32_t d_tmem = tmem_base + ((kc >= rc0) ? BN : as * BN);
+        const int kfirst = (kc >= rc0) ? rc0 : 0;
         mbar_wait(&full_bar[stage], phase);
         if (tl && lane == 0 && kc == 0 && tile == (int)blockIdx.x) tl[3] = clock64();
         tc_fence_after();
@@ -287,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kc - kfirst) | k) != 0);
           umma_commit(&empty_bar[stage]);
           if (kc == total_chunks - 1) umma_commit(&tfull_bar[as]);
         }
@@ -295,8 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (tl && lane == 0) tl[4] = clock64();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (rc0 < total_chunks) { aphase ^= 1; }            // dual accumulator: one TMEM stage (as stays 0)
+      else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   } else if (warp >= 3) {
     // ===================================== epilogue =========================================
@@ -430,6 +439,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __syncwarp();
           }
         }
+        if constexpr (EPI == EPI_STATS) {
+          if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
+            __half* rob = p.res_out + (size_t)rw0 * p.ldo + cbase;
+            tmem_ld32(taddr + BN, vbuf[0]);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              float* v = vbuf[c & 1];
+              tmem_ld_wait();
+              if (c + 1 < NCH) tmem_ld32(taddr + BN + (c + 1) * 32, vbuf[(c + 1) & 1]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = lds_f4(spar + (512 + cbase + c * 32 + 4 * j) * 4);
+                v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+              epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
+            }
+          }
+        }
         if constexpr (EPI == EPI_LN) {
           // LayerNorm over the full BN-wide row: combine the two column halves through smem
           const uint32_t red = smem_u32(s_red) + (as ? GEMM_BM * 16 : 0);  // double-buffered by accumulator stage
@@ -542,8 +569,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (EPI == EPI_STATS && p.res_chunk0 > 0) { aphase ^= 1; }   // dual accumulator: single TMEM stage
+      else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   }
 

@@ -114,9 +114,9 @@ struct WEntry {
 struct StageW {
   int nsrc;
   int src_cols[2];  // padded columns of each input source
-  size_t c1, c2, res, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets)
+  size_t c1, c2, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets); c1 also holds res_conv
   size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
-  CUtensorMap m_c1, m_c2, m_res, m_qkv, m_wo, m_ff1, m_ff2;
+  CUtensorMap m_c1, m_c2, m_qkv, m_wo, m_ff1, m_ff2;
   CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 64, 4}: one hidden chunk of the fused tail (ff_tail.cuh)
 };
 
@@ -214,9 +214,10 @@ static void build_tables(MttsHandle* h) {
     h->entries.push_back(std::move(e));
   };
   // conv k3 weight (N, Ci, 3) -> [N, 3*CiTot] tap-major
-  auto conv3_ops = [&](size_t dst, int N, int Ci, int CiTot) {
+  auto conv3_ops = [&](size_t dst, int N, int Ci, int CiTot, int ld = 0) {
     std::vector<PackOp> v;
-    for (int t = 0; t < 3; ++t) v.push_back(op_h(dst, N, Ci, (long)Ci * 3, 3, t, 0, 3 * CiTot, t * CiTot));
+    if (ld == 0) ld = 3 * CiTot;
+    for (int t = 0; t < 3; ++t) v.push_back(op_h(dst, N, Ci, (long)Ci * 3, 3, t, 0, ld, t * CiTot));
     return v;
   };
 
@@ -236,7 +237,7 @@ static void build_tables(MttsHandle* h) {
     if (s == 0) { w.nsrc = 1; w.src_cols[0] = h->cinp; w.src_cols[1] = 0; ci_real = Cin; ci_tot = h->cinp; }
     else if (s < 4) { w.nsrc = 1; w.src_cols[0] = C; w.src_cols[1] = 0; ci_real = C; ci_tot = C; }
     else { w.nsrc = 2; w.src_cols[0] = C; w.src_cols[1] = C; ci_real = 2 * C; ci_tot = 2 * C; }
-    w.c1 = alloc(2ull * C * 3 * ci_tot); w.c2 = alloc(2ull * C * 3 * C); w.res = alloc(2ull * C * ci_tot);
+    w.c1 = alloc(2ull * C * 4 * ci_tot); w.c2 = alloc(2ull * C * 3 * C);  // c1 = [conv taps (3*ci) | res_conv (ci)] along K
     w.qkv = alloc(2ull * 3 * AD * C); w.wo = alloc(2ull * C * AD);
     w.ff1 = alloc(2ull * FD * C); w.ff2 = alloc(2ull * C * FD);
     size_t* f256[] = {&w.c1_b, &w.gn1_g, &w.gn1_b, &w.c2_b, &w.gn2_g, &w.gn2_b, &w.res_b, &w.ln1_g,
@@ -247,7 +248,7 @@ static void build_tables(MttsHandle* h) {
     const std::string r = std::string(kStageNames[s]) + ".0", t = std::string(kStageNames[s]) + ".1.0";
     add(r + ".mlp.1.weight", (int64_t)C * TD, {op_f(h->mlpW + sizeof(float) * (size_t)s * C * TD, C * TD)});
     add(r + ".mlp.1.bias", C, {op_f(h->mlpB + sizeof(float) * (size_t)s * C, C)});
-    add(r + ".block1.block.0.weight", (int64_t)C * ci_real * 3, conv3_ops(w.c1, C, ci_real, ci_tot));
+    add(r + ".block1.block.0.weight", (int64_t)C * ci_real * 3, conv3_ops(w.c1, C, ci_real, ci_tot, 4 * ci_tot));
     add(r + ".block1.block.0.bias", C, {op_f(w.c1_b, C)});
     add(r + ".block1.block.1.weight", C, {op_f(w.gn1_g, C)});
     add(r + ".block1.block.1.bias", C, {op_f(w.gn1_b, C)});
@@ -255,7 +256,7 @@ static void build_tables(MttsHandle* h) {
     add(r + ".block2.block.0.bias", C, {op_f(w.c2_b, C)});
     add(r + ".block2.block.1.weight", C, {op_f(w.gn2_g, C)});
     add(r + ".block2.block.1.bias", C, {op_f(w.gn2_b, C)});
-    add(r + ".res_conv.weight", (int64_t)C * ci_real, {op_h(w.res, C, ci_real, ci_real, 1, 0, 0, ci_tot, 0)});
+    add(r + ".res_conv.weight", (int64_t)C * ci_real, {op_h(w.c1, C, ci_real, ci_real, 1, 0, 0, 4 * ci_tot, 3 * ci_tot)});
     add(r + ".res_conv.bias", C, {op_f(w.res_b, C)});
     add(t + ".norm1.weight", C, {op_f(w.ln1_g, C)});
     add(t + ".norm1.bias", C, {op_f(w.ln1_b, C)});
@@ -312,9 +313,8 @@ static int build_weight_maps(MttsHandle* h) {
   for (int s = 0; s < 6; ++s) {
     StageW& w = h->st[s];
     const int ci = w.src_cols[0] + w.src_cols[1];
-    if (make_map(&w.m_c1, a + w.c1, C, 3 * ci, 3 * ci, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_c1, a + w.c1, C, 4 * ci, 4 * ci, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_c2, a + w.c2, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-    if (make_map(&w.m_res, a + w.res, C, ci, ci, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_qkv, a + w.qkv, 384, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
@@ -514,19 +514,18 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
   base.M = lc.rows; base.rowb = lc.rowb; base.Lp = lc.Lp; base.mask_mul = 1; base.mask_nstep = 0;
   base.stats_part = part; base.S = w.S; base.ldo = C; base.ldr = C;
 
-  // conv1 (k3) -> y, GroupNorm partial sums
+  // conv1 (k3) -> y with GroupNorm partial sums, and res_conv (1x1) -> res from the same activation tiles:
+  // K chunks = [3 taps x sources | 1 x sources], the last group accumulates into the second TMEM accumulator
   {
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, sw.src_cols[0], sw.src_cols[1]);
+    int conv_chunks = 0;
+    for (int i = 0; i < p.num_segs; ++i) conv_chunks += p.seg[i].nchunks;
+    p.seg[p.num_segs++] = GemmSeg{0, 0, 0, sw.src_cols[0] / 64};
+    if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
+    p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
     p.n_tiles = 1; p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 3 * ci_real)) return e;
-  }
-  // res_conv (1x1) -> res
-  {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, sw.src_cols[0], sw.src_cols[1]);
-    p.n_tiles = 1; p.bias = F(sw.res_b); p.out = H(w.res);
-    if (int e = launch_gemm<256, EPI_PLAIN>(h, in0, in1, sw.m_res, p, stream, fr * C * ci_real)) return e;
+    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
   }
   const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
@@ -743,9 +742,11 @@ struct Chunk { int b0, nb; size_t ws_off; };
 static int pick_nsub(const MttsHandle* h, int B, int T) {
   int n = h->nsub_override;
   if (n <= 0) {
-    // aim at >= ~20 row tiles of 128 per chain at level T, at most 8 chains
+    // two chains once each still fills most SMs with one row tile per CTA at level T: the second chain's
+    // kernels run in the SMs the first leaves idle (wave tails, T/2-level kernels); more chains only add
+    // launches (measured: profiles/r01_chain_sweep.txt)
     const long rows = (long)B * (T + 2);
-    n = (int)(rows / 2560);
+    n = rows >= 16384 ? 2 : 1;
   }
   if (n > 8) n = 8;
   if (n > B) n = B;

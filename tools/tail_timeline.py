@@ -12,7 +12,7 @@ from matcha_tts_b200 import Decoder, _lib  # noqa: E402
 
 def main():
     B, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 344)
-    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 6 + 8 + 1 + 8      # prologue + stage 0 + down conv + stage 1
+    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 6 + 7 + 1 + 7      # prologue + stage 0 + down conv + stage 1
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     dec = Decoder(160, 80, num_heads=2).to(dev)
