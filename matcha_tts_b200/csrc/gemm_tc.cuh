@@ -102,6 +102,7 @@ struct GemmParams {
   // debug: per-CTA timeline [gridDim.x][16] (clock64 / globaltimer stamps), null in production
   long long* tl;
   int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
+  int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
 };
 
 template <int BN, int EPI = EPI_PLAIN>
@@ -219,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       s_par[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
       if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
-      if constexpr (EPI == EPI_STATS) if (p.res_chunk0 > 0 && i < BN) s_par[512 + i] = p.res_bias[i];
+      if constexpr (EPI == EPI_STATS) if (p.res_chunk0 > 0 && i < 256) s_par[512 + i] = p.res_bias[i];
     }
   }
   tc_fence_before();
@@ -247,6 +248,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+  }
+
+  if (warp == 0 && (int)blockIdx.x < total_tiles && p.a_prefetch) {
+    // warm the TLB / L2 path of this CTA's first activation tiles while the previous kernel drains
+    if (elect_one()) {
+      const int r0 = ((int)blockIdx.x / p.n_tiles) * GEMM_BM;
+      int kc = 0;
+      for (int s = 0; s < p.num_segs && kc < STAGES; ++s) {
+        const GemmSeg sg = p.seg[s];
+        for (int c = 0; c < sg.nchunks && kc < STAGES; ++c, ++kc)
+          tma_prefetch_2d(sg.src ? &tmA1 : &tmA0, sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
+      }
+    }
+    __syncwarp();
   }
 
   pdl_wait();  // everything below touches memory the previous kernel may still be using
@@ -337,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint4 rr[4];
         if (has_res) epi_resid_issue(rr, lane, rbase, p.ldr, rows_valid);
         float mrow = 1.f;
-        if constexpr (EPI == EPI_PLAIN) if (p.rowmask && row_ok) mrow = p.rowmask[(size_t)row * p.mask_mul + n_tile * p.mask_nstep];
+        if constexpr (EPI == EPI_PLAIN) if (p.rowmask && row_ok) mrow = p.rowmask[(size_t)row * p.mask_mul + (n0 >> 8) * p.mask_nstep];  // ConvT: one output phase per 256 columns
         int myb = -1;
         if constexpr (EPI == EPI_STATS) if (row_ok) myb = p.rowb[row];
 
@@ -410,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 gs[j] = x;
               }
               if (lane == 0) {
-                float* dst = p.stats_part + ((size_t)b0 * p.S + (wb - ((b0 * p.Lp) >> 5))) * 16 + hcol * 2 * NCH;
+                float* dst = p.stats_part + ((size_t)b0 * p.S + (wb - ((b0 * p.Lp) >> 5))) * 16 + (((n0 + cbase) >> 5) << 1);
 #pragma unroll
                 for (int j = 0; j < 2 * NCH; ++j) dst[j] = gs[j];
               }
@@ -428,20 +443,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int i = 0; i < 32; ++i) {
                 const int bi = (int)lds_u32(sb + i * 4);
                 if (bi != cur) {
-                  if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + hcol * 2 * NCH + lane] = acc;
+                  if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + (((n0 + cbase) >> 5) << 1) + lane] = acc;
                   cur = bi;
                   acc = 0.f;
                 }
                 acc += lds_f32(sf + (i * 9 + lane) * 4);
               }
-              if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + hcol * 2 * NCH + lane] = acc;
+              if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + (((n0 + cbase) >> 5) << 1) + lane] = acc;
             }
             __syncwarp();
           }
         }
         if constexpr (EPI == EPI_STATS) {
           if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
-            __half* rob = p.res_out + (size_t)rw0 * p.ldo + cbase;
+            __half* rob = p.res_out + (size_t)rw0 * p.ldo + n0 + cbase;
             tmem_ld32(taddr + BN, vbuf[0]);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -450,7 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               if (c + 1 < NCH) tmem_ld32(taddr + BN + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b4 = lds_f4(spar + (512 + cbase + c * 32 + 4 * j) * 4);
+                const float4 b4 = lds_f4(spar + (512 + n0 + cbase + c * 32 + 4 * j) * 4);
                 v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
               }
               epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);

@@ -117,6 +117,7 @@ struct StageW {
   size_t c1, c2, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets); c1 also holds res_conv
   size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
   CUtensorMap m_c1, m_c2, m_qkv, m_wo, m_ff1, m_ff2;
+  CUtensorMap m_c1h, m_c2h;  // same weights, 128-row boxes (BN = 128 tiles)
   CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 64, 4}: one hidden chunk of the fused tail (ff_tail.cuh)
 };
 
@@ -161,10 +162,14 @@ struct MttsHandle {
   size_t w_down0, w_down1, w_up0, w_up1, w_fin, w_proj;
   size_t b_down0, b_down1, b_up0, b_up1, b_fin, gnf_g, gnf_b, b_proj;
   CUtensorMap m_down0, m_down1, m_up0, m_up1, m_fin, m_proj;
+  CUtensorMap m_down0h, m_down1h, m_up0h, m_up1h, m_finh;  // 128-row boxes
   bool maps_ready = false;
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
   int launch_count = 0, launch_limit = -1;
+  int conv_bn = 256;       // MTTS_BN: N tile of the conv GEMMs at level T (256, or 128: twice the CTAs / half the tile)
+  int conv_bn_h = 256;     // MTTS_BN_H: same at level T/2 (87 row tiles at B=64, T=344)
+  bool a_prefetch = true;  // MTTS_NO_APREFETCH=1: no early L2 prefetch of the first activation tiles
   bool w_hint = true;      // MTTS_NO_WHINT=1: load weights without the L2 evict_last hint
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
@@ -315,6 +320,8 @@ static int build_weight_maps(MttsHandle* h) {
     const int ci = w.src_cols[0] + w.src_cols[1];
     if (make_map(&w.m_c1, a + w.c1, C, 4 * ci, 4 * ci, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_c2, a + w.c2, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+    if (make_map(&w.m_c1h, a + w.c1, C, 4 * ci, 4 * ci, 128)) return MTTS_ECUDA;
+    if (make_map(&w.m_c2h, a + w.c2, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
     if (make_map(&w.m_qkv, a + w.qkv, 384, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
@@ -327,6 +334,11 @@ static int build_weight_maps(MttsHandle* h) {
   if (make_map(&h->m_up1, a + h->w_up1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
   if (make_map(&h->m_fin, a + h->w_fin, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
   if (make_map(&h->m_proj, a + h->w_proj, 128, C, C, 128)) return MTTS_ECUDA;
+  if (make_map(&h->m_down0h, a + h->w_down0, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
+  if (make_map(&h->m_down1h, a + h->w_down1, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
+  if (make_map(&h->m_up0h, a + h->w_up0, 2 * C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
+  if (make_map(&h->m_up1h, a + h->w_up1, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
+  if (make_map(&h->m_finh, a + h->w_fin, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
   h->maps_ready = true;
   return 0;
 }
@@ -471,6 +483,7 @@ static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& 
   GemmParams pp = p;
   pp.tl = nullptr;
   pp.w_hint = h->w_hint ? 1 : 0;
+  pp.a_prefetch = h->a_prefetch ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI>::TOTAL, stream, a0, a1, wmap, pp));
   launched(h);
@@ -508,6 +521,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
   float* part = reinterpret_cast<float*>(ws + w.part);
   const float* te6 = reinterpret_cast<const float*>(ws + w.te6);
 
+  const int conv_bn = lc.lv ? h->conv_bn_h : h->conv_bn;
   const double fr = 2.0 * w.B * (double)lc.L;   // algorithmic FLOPs = fr * N * K (valid rows, unpadded K/N)
   const int ci_real = (s == 0) ? h->cfg.in_channels : sw.src_cols[0] + sw.src_cols[1];
   GemmParams base{};
@@ -524,8 +538,9 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     p.seg[p.num_segs++] = GemmSeg{0, 0, 0, sw.src_cols[0] / 64};
     if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
     p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
-    p.n_tiles = 1; p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
+    p.bias = F(sw.c1_b); p.out = H(w.y);
+    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1h, p, stream, fr * C * 4 * ci_real)) return e; }
+    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
   }
   const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
@@ -540,8 +555,9 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
   {
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
-    p.n_tiles = 1; p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
+    p.bias = F(sw.c2_b); p.out = H(w.y);
+    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2h, p, stream, fr * C * 3 * C)) return e; }
+    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
   }
   // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
   {
@@ -624,8 +640,8 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
               reinterpret_cast<const int*>(ws + w.rowbH), reinterpret_cast<const int*>(ws + w.npadH)};
   float* part = reinterpret_cast<float*>(ws + w.part);
 
-  auto level_conv = [&](const CUtensorMap& in, const CUtensorMap& wmap, size_t bias, const LevelCtx& lc, __half* out,
-                        int mode) -> int {
+  auto level_conv = [&](const CUtensorMap& in, const CUtensorMap& wmap, const CUtensorMap& wmaph, size_t bias,
+                        const LevelCtx& lc, __half* out, int mode) -> int {
     GemmParams p{};
     p.rowb = lc.rowb; p.Lp = lc.Lp; p.ldr = C; p.bias = F(bias); p.out = out; p.rowmask = lc.mask;
     p.mask_mul = 1; p.mask_nstep = 0; p.ldo = C; p.n_tiles = 1; p.M = lc.rows;
@@ -642,15 +658,16 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     }
     // k3 convs: out rows * 256 * 768; ConvTranspose: B*H input rows * 512 outputs * 512 (two 2-tap phases)
     const double af = (mode == 2) ? 2.0 * w.B * (double)w.H * 512 * 512 : 2.0 * w.B * (double)lc.L * C * 3 * C;
+    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmaph, p, stream, af); }
     return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream, af);
   };
 
   // down 0 @T
   if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
+  if (int e = level_conv(P.skip0_pair, h->m_down0, h->m_down0h, h->b_down0, lH, H(w.xD0), 1)) return e;
   // down 1 @T/2
   if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
+  if (int e = level_conv(P.skip1, h->m_down1, h->m_down1h, h->b_down1, lH, H(w.xD1), 0)) return e;
   // mid
   if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
   if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
@@ -658,18 +675,19 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
   if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
   {
     LevelCtx lc = lT;  // mask of the OUTPUT rows (level T), indexed 2*r + phase
-    if (int e = level_conv(P.xU0s, h->m_up0, h->b_up0, lc, H(w.xU0), 2)) return e;
+    if (int e = level_conv(P.xU0s, h->m_up0, h->m_up0h, h->b_up0, lc, H(w.xU0), 2)) return e;
   }
   // up 1 @T : cat[x, skip0]
   if (int e = run_stage(h, P, 5, lT, P.xU0, P.skip0, H(w.xU1s), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.xU1s, h->m_up1, h->b_up1, lT, H(w.xF), 0)) return e;
+  if (int e = level_conv(P.xU1s, h->m_up1, h->m_up1h, h->b_up1, lT, H(w.xF), 0)) return e;
   // final block + projection + ODE update
   {
     GemmParams p{};
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
-    p.n_tiles = 1; p.bias = F(h->b_fin); p.out = H(w.y);
-    if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e;
+    p.bias = F(h->b_fin); p.out = H(w.y);
+    if (h->conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_finh, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
+    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
@@ -812,6 +830,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
+  if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
+  if (const char* e = getenv("MTTS_BN_H")) h->conv_bn_h = atoi(e) == 128 ? 128 : 256;
+  if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   build_tables(h);
@@ -831,7 +852,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     int e = 0;
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
     e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV>(); e |= set_gemm_attr<128, EPI_FINAL>();
-    e |= set_gemm_attr<128, EPI_PLAIN>();
+    e |= set_gemm_attr<128, EPI_PLAIN>(); e |= set_gemm_attr<128, EPI_STATS>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }

@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
       : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination, no barrier).  Issued BEFORE griddepcontrol.wait for the
+// first activation tiles of a CTA: L2 is the coherence point, so a line the previous kernel rewrites later is
+// simply updated -- the prefetch only warms the TLB / L2 path that the first real load would otherwise pay for.
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
+}
+
 // L2 eviction-priority policies for TMA loads: weights are re-read by every CTA of every launch of every
 // ODE step and should stay resident (evict_last) while ~0.4 GB of activations stream through L2 per step.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
