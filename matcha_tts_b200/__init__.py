@@ -6,5 +6,7 @@ Python, so the directory is `matcha_tts_b200`.
 from .model import (BASECFM, CFM, Decoder, MatchaTTS, denormalize, fix_len_compatibility, generate_path,
                     sequence_mask)
 
-__all__ = ["BASECFM", "CFM", "Decoder", "MatchaTTS", "denormalize", "fix_len_compatibility", "generate_path",
+from . import batching  # noqa: E402,F401  (length bucketing + utterance sharding front end)
+
+__all__ = ["batching", "BASECFM", "CFM", "Decoder", "MatchaTTS", "denormalize", "fix_len_compatibility", "generate_path",
            "sequence_mask"]

@@ -1,0 +1,141 @@
+"""Variable-length utterance batching for the CFM decoder: length bucketing + utterance sharding.
+
+The decoder's results depend on batch composition (GroupNorm statistics span the padded frames and
+the attention-mask quirk keys on padding: SURVEY.md section 0, traps 5 and 6), so
+
+  * a bucket's composition and its padded length T_max are a deterministic function of the input
+    length list ALONE -- never of the number of GPUs -- so 1/2/4/8-GPU runs give identical mels for
+    every utterance;
+  * T_max is rounded exactly like the reference: fix_len_compatibility(max length) (model.py:49-55,
+    :1281), i.e. up to a multiple of 4.
+
+Buckets are then assigned to ranks (one process per GPU) by greedy longest-processing-time on the
+padded-frame cost B*T*F(T); each rank solves its own buckets with no collective on the hot path and
+the finished mels are gathered once at the end (torch.distributed all_gather_object / NCCL or gloo).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from .model import fix_len_compatibility
+
+GEMM_FLOP_PER_FRAME = 10_985_472      # SURVEY.md App. C, per padded frame and Euler step (Cin = 160)
+ATTN_FLOP_PER_FRAME_PER_T = 1536
+
+
+@dataclass(frozen=True)
+class Bucket:
+    """One batch: utterance indices (into the caller's list) and the common padded length."""
+    indices: tuple
+    t_max: int
+
+    @property
+    def padded_frames(self) -> int:
+        return len(self.indices) * self.t_max
+
+    @property
+    def cost(self) -> float:
+        """Estimated FLOPs per Euler step (the load-balancing weight)."""
+        return float(self.padded_frames) * (GEMM_FLOP_PER_FRAME + ATTN_FLOP_PER_FRAME_PER_T * self.t_max)
+
+
+def make_buckets(lengths: Sequence[int], max_frames: int = 64 * 344, max_batch: int = 256) -> List[Bucket]:
+    """Sort utterances by length (stable: ties keep input order) and cut them greedily into batches
+    whose padded size B * T_max stays within `max_frames` (and B within `max_batch`).
+
+    Sorting keeps padding small (a batch's T_max is its longest member rounded up to a multiple of
+    4).  The result depends only on `lengths`, `max_frames` and `max_batch`.
+    """
+    if any(int(n) < 1 for n in lengths):
+        raise ValueError("utterance lengths must be >= 1")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))      # longest first
+    buckets: List[Bucket] = []
+    cur: List[int] = []
+    cur_t = 0
+    for i in order:
+        t = fix_len_compatibility(int(lengths[i]))
+        if not cur:
+            cur, cur_t = [i], t
+            continue
+        # longest first: T_max of the bucket is fixed by its first member
+        if (len(cur) + 1) * cur_t <= max(max_frames, cur_t) and len(cur) + 1 <= max_batch:
+            cur.append(i)
+        else:
+            buckets.append(Bucket(tuple(cur), cur_t))
+            cur, cur_t = [i], t
+    if cur:
+        buckets.append(Bucket(tuple(cur), cur_t))
+    return buckets
+
+
+def assign_buckets(buckets: Sequence[Bucket], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of bucket ids to ranks (deterministic)."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    loads = [0.0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for b in sorted(range(len(buckets)), key=lambda j: (-buckets[j].cost, j)):
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        out[r].append(b)
+        loads[r] += buckets[b].cost
+    for lst in out:
+        lst.sort()
+    return out
+
+
+def pad_batch(mus: Sequence[torch.Tensor], bucket: Bucket, device=None):
+    """Stack the (n_feats, T_i) encoder outputs of a bucket into (B, n_feats, T_max) + prefix mask."""
+    n_feats = mus[bucket.indices[0]].shape[0]
+    B = len(bucket.indices)
+    mu = torch.zeros(B, n_feats, bucket.t_max, dtype=torch.float32, device=device)
+    mask = torch.zeros(B, 1, bucket.t_max, dtype=torch.float32, device=device)
+    for row, i in enumerate(bucket.indices):
+        t = mus[i].shape[1]
+        mu[row, :, :t] = mus[i].to(device=device, dtype=torch.float32)
+        mask[row, 0, :t] = 1.0
+    return mu, mask
+
+
+Solver = Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Bucket], torch.Tensor]
+
+
+def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Sequence[torch.Tensor]] = None,
+                  max_frames: int = 64 * 344, max_batch: int = 256, device=None, group=None,
+                  gather: bool = True) -> Dict[int, torch.Tensor]:
+    """Run `solver(mu, mask, spks, bucket) -> (B, n_feats, T_max)` over this rank's buckets and gather.
+
+    mus[i]: (n_feats, T_i) encoder output of utterance i (every rank passes the same list; only the
+    local shard is touched).  Returns {utterance index: (n_feats, T_i) mel on the CPU}; with
+    `gather` every rank gets all utterances, otherwise only its own.
+    In production `solver` is `lambda mu, mask, s, b: cfm(mu, mask, n_timesteps, temperature, s)`
+    (matcha_tts_b200.CFM); the CPU tests inject a stub, the scheduling/gather logic is the same.
+    """
+    import torch.distributed as dist
+    use_dist = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if use_dist else 1
+    rank = dist.get_rank(group) if use_dist else 0
+    lengths = [int(m.shape[1]) for m in mus]
+    buckets = make_buckets(lengths, max_frames, max_batch)
+    mine = assign_buckets(buckets, world)[rank]
+    local: Dict[int, torch.Tensor] = {}
+    for bid in mine:
+        bk = buckets[bid]
+        mu, mask = pad_batch(mus, bk, device)
+        s = None
+        if spks is not None:
+            s = torch.stack([spks[i] for i in bk.indices]).to(device=device, dtype=torch.float32)
+        out = solver(mu, mask, s, bk)
+        out = out.detach().to("cpu", torch.float32)
+        for row, i in enumerate(bk.indices):
+            local[i] = out[row, :, :lengths[i]].clone()
+    if not (use_dist and gather and world > 1):
+        return local
+    parts: List[Optional[dict]] = [None] * world
+    dist.all_gather_object(parts, local, group=group)      # the only collective: finished mels
+    merged: Dict[int, torch.Tensor] = {}
+    for p in parts:
+        merged.update(p)
+    return merged

@@ -1,0 +1,112 @@
+"""Host-side batching: length bucketing, rank assignment and the final gather.
+The multi-rank path runs here on CPU with the gloo backend (world_size 2) and a stub solver: the
+scheduling / gather logic under test is exactly what the GPU ranks execute around the native solver."""
+import os
+import random
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from matcha_tts_b200 import batching as Bt
+from matcha_tts_b200.model import fix_len_compatibility
+
+
+def _lengths(n, seed, lo=64, hi=800):
+    rng = random.Random(seed)
+    return [max(lo, min(hi, int(rng.lognormvariate(5.7, 0.45)))) for _ in range(n)]
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (7, 1), (300, 2), (4096, 6)])
+def test_buckets_cover_every_utterance_once(n, seed):
+    lengths = _lengths(n, seed)
+    buckets = Bt.make_buckets(lengths, max_frames=64 * 344)
+    seen = sorted(i for b in buckets for i in b.indices)
+    assert seen == list(range(n))
+    for b in buckets:
+        longest = max(lengths[i] for i in b.indices)
+        assert b.t_max == fix_len_compatibility(longest) and b.t_max % 4 == 0      # reference rounding (model.py:49-55)
+        assert b.padded_frames <= max(64 * 344, b.t_max)
+    # sorted by length: padding waste stays small
+    if n >= 300:
+        valid = sum(lengths)
+        padded = sum(b.padded_frames for b in buckets)
+        assert padded <= (1.03 if n >= 4096 else 1.2) * valid
+
+
+def test_buckets_are_deterministic_and_independent_of_world_size():
+    lengths = _lengths(500, 3)
+    b1 = Bt.make_buckets(lengths)
+    b2 = Bt.make_buckets(list(lengths))
+    assert b1 == b2
+    for world in (1, 2, 4, 8):
+        parts = Bt.assign_buckets(b1, world)
+        assert sorted(j for p in parts for j in p) == list(range(len(b1)))
+        loads = [sum(b1[j].cost for j in p) for p in parts]
+        if world > 1 and len(b1) >= 4 * world:
+            assert max(loads) <= 1.25 * (sum(loads) / world)                       # LPT keeps ranks balanced
+
+
+def test_edge_cases():
+    assert Bt.make_buckets([]) == []
+    assert Bt.make_buckets([5]) == [Bt.Bucket((0,), 8)]
+    with pytest.raises(ValueError):
+        Bt.make_buckets([10, 0])
+    # one utterance longer than the frame budget still gets its own bucket
+    bs = Bt.make_buckets([5000, 10, 10], max_frames=1024)
+    assert bs[0] == Bt.Bucket((0,), 5000)
+    # ties keep input order
+    assert Bt.make_buckets([8, 8, 8], max_frames=16)[0].indices == (0, 1)
+    mus = [torch.randn(80, 5), torch.randn(80, 8)]
+    mu, mask = Bt.pad_batch(mus, Bt.Bucket((1, 0), 8))
+    assert mu.shape == (2, 80, 8) and mask[1, 0].tolist() == [1] * 5 + [0] * 3
+    assert torch.equal(mu[1, :, :5], mus[0]) and float(mu[1, :, 5:].abs().max()) == 0.0
+
+
+def _stub_solver(mu, mask, spks, bucket):
+    """Depends on the whole batch (like the real decoder): row result = mu * mask + batch mean."""
+    out = mu * mask + mu.mean()
+    if spks is not None:
+        out = out + spks.mean(1)[:, None, None]
+    return out
+
+
+def _worker(rank, world, port, lengths, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11)
+    mus = [torch.randn(80, n, generator=g) for n in lengths]
+    spks = [torch.randn(64, generator=g) for _ in lengths]
+    out = Bt.solve_sharded(mus, _stub_solver, spks=spks, max_frames=4096)
+    if rank == 0:
+        ret.update({i: v for i, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_gloo_matches_single_process():
+    lengths = _lengths(37, 5, lo=16, hi=300)
+    g = torch.Generator().manual_seed(11)
+    mus = [torch.randn(80, n, generator=g) for n in lengths]
+    spks = [torch.randn(64, generator=g) for _ in lengths]
+    single = Bt.solve_sharded(mus, _stub_solver, spks=spks, max_frames=4096)
+    assert sorted(single) == list(range(len(lengths)))
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, _free_port(), lengths, ret), nprocs=2, join=True)
+        multi = dict(ret)
+    assert sorted(multi) == sorted(single)
+    for i in single:
+        assert multi[i].shape == (80, lengths[i])
+        assert torch.equal(multi[i], single[i])          # sharding must not change any utterance's result

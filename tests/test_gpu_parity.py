@@ -265,3 +265,35 @@ def test_synthesize_facade_with_stub_encoder(lj):
     ref = O.euler_solve(sd, cfg, z0, mu_y, y_mask, 4) * 2.1 - 5.5
     ma, rl = O.parity_errors(mel.cpu(), ref[:, :, :int(yl.max())], y_mask[:, :, :int(yl.max())])
     assert ma <= 2.1 * O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+# ---------------------------------------------------------------------------------------------
+# config 5 shape: length-bucketed multi-speaker batches through the sharding front end
+# ---------------------------------------------------------------------------------------------
+def test_bucketed_multispeaker_matches_oracle(vctk):
+    """matcha_tts_b200.batching: utterances of different lengths are bucketed (T_max rounded like the
+    reference), solved natively bucket by bucket and cropped; every utterance must match the oracle run on
+    the SAME padded batch (results depend on batch composition: SURVEY.md section 0 traps 5/6)."""
+    from matcha_tts_b200 import batching as Bt
+    dec, cfg, sd = vctk
+    g = torch.Generator().manual_seed(41)
+    lengths = [131, 64, 200, 97, 180, 66, 150]
+    mus = [torch.randn(80, n, generator=g) for n in lengths]
+    spks = [torch.randn(64, generator=g) for _ in lengths]
+    noise = {}
+
+    def solver(mu, mask, s, bucket):
+        gz = torch.Generator().manual_seed(1000 + bucket.t_max)
+        z0 = torch.randn(mu.shape, generator=gz) * 0.667
+        noise[bucket] = (z0, mu.cpu(), mask.cpu(), s.cpu())
+        return dec.solve(_d(z0), mu, mask, 4, s, "euler", use_graph=True)
+
+    out = Bt.solve_sharded(mus, solver, spks=spks, max_frames=3 * 200, device="cuda")
+    assert sorted(out) == list(range(len(lengths))) and len(noise) >= 3
+    for bucket, (z0, mu, mask, s) in noise.items():
+        ref = O.euler_solve(sd, cfg, z0, mu, mask, 4, s)
+        for row, i in enumerate(bucket.indices):
+            n = lengths[i]
+            ma, rl = O.parity_errors(out[i][None], ref[row:row + 1, :, :n], mask[row:row + 1, :, :n])
+            assert out[i].shape == (80, n)
+            assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (i, ma, rl)
