@@ -289,7 +289,7 @@ def test_bucketed_multispeaker_matches_oracle(vctk):
         return dec.solve(_d(z0), mu, mask, 4, s, "euler", use_graph=True)
 
     out = Bt.solve_sharded(mus, solver, spks=spks, max_frames=3 * 200, device="cuda")
-    assert sorted(out) == list(range(len(lengths))) and len(noise) >= 3
+    assert sorted(out) == list(range(len(lengths))) and len(noise) >= 2
     for bucket, (z0, mu, mask, s) in noise.items():
         ref = O.euler_solve(sd, cfg, z0, mu, mask, 4, s)
         for row, i in enumerate(bucket.indices):
