@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
 
 METRIC = "mel-frames/sec for CFM decoder sampling (10 Euler steps)"
 UNIT = "mel-frames/s"

@@ -48,11 +48,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   pdl_launch_dependents();
-  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int rowbase = b * p.Lp;
   const int my_t = q0 + tid;  // query frame handled by this thread
+
+  // barriers / TMEM are set up while the previous kernel drains (both paths; the quirk path frees TMEM again)
+  if (tid == 0) {
+    mbar_init(&bar_kv[0], 1);
+    mbar_init(&bar_kv[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVT);
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // ---------------- quirk path: utterance has masked keys -> uniform mean of V over them ----------
   const int npad = p.npad[b];
@@ -74,22 +91,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         dst[j] = make_uint4(pack_h2(s_mean[8 * j], s_mean[8 * j + 1]), pack_h2(s_mean[8 * j + 2], s_mean[8 * j + 3]),
                             pack_h2(s_mean[8 * j + 4], s_mean[8 * j + 5]), pack_h2(s_mean[8 * j + 6], s_mean[8 * j + 7]));
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
     return;
   }
 
   // ---------------- full path: flash-style softmax(Q K^T) V on tcgen05 ----------------------------
-  if (tid == 0) {
-    mbar_init(&bar_kv[0], 1);
-    mbar_init(&bar_kv[1], 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;         // 128 columns
   const uint32_t tO = tmem_base + 128;   // 64 columns
   const uint32_t lane_off = uint32_t(warp * 32) << 16;
@@ -104,9 +112,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_load_2d(sV + buf * 16384, &tmVT, &bar_kv[buf], j * 128, (b * 2 + h) * 64);
     tma_load_2d(sV + buf * 16384 + 8192, &tmVT, &bar_kv[buf], j * 128 + 64, (b * 2 + h) * 64);
   };
-  if (tid == 0) {
-    issue_kv(0);
-    if (nkv > 1) issue_kv(1);
+  if (warp == 0) {  // converged warp, one elected lane issues (uniform operands)
+    if (elect_one()) {
+      issue_kv(0);
+      if (nkv > 1) issue_kv(1);
+    }
+    __syncwarp();
   }
 
   constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);
@@ -119,16 +130,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   for (int j = 0; j < nkv; ++j) {
     const int buf = j & 1;
-    if (tid == 0) {
+    if (warp == 0) {
       mbar_wait(&bar_kv[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
       const uint64_t dk = umma_desc_sw128(smem_u32(sK + buf * 16384));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      umma_commit(bar_s);
+        for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
 
@@ -176,18 +189,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     fence_proxy_async_smem();  // P written with generic-proxy stores, read by the tensor core
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dv0 = umma_desc_sw128(smem_u32(sV + buf * 16384));
+      if (elect_one()) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint64_t dp = umma_desc_sw128(smem_u32(sP + c * 16384));
-        const uint64_t dv = umma_desc_sw128(smem_u32(sV + buf * 16384 + c * 8192));
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc_o, (c | k) != 0);
+          for (int k = 0; k < 4; ++k)   // descriptor address field counts 16-byte units
+            umma_f16(tO, dp0 + c * (16384 >> 4) + 2 * k, dv0 + c * (8192 >> 4) + 2 * k, idesc_o, (c | k) != 0);
+        umma_commit(bar_o);
       }
-      umma_commit(bar_o);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
     {
@@ -200,7 +214,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < 32; ++i) acc[c * 32 + i] += o[i];
       }
     }
-    if (tid == 0 && j + 2 < nkv) issue_kv(j + 2);  // both MMAs that read buffer `buf` have completed
+    if (warp == 0 && j + 2 < nkv) {  // both MMAs that read buffer `buf` have completed
+      if (elect_one()) issue_kv(j + 2);
+      __syncwarp();
+    }
     tc_fence_before();
     __syncwarp();
   }
