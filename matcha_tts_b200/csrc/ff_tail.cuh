@@ -64,20 +64,6 @@ constexpr int TAIL_OFF_RED = TAIL_OFF_PAR + TAIL_PAR_FLOATS * 4;      // 212992:
 constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;       // 217088
 constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;                         // 217344
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
-                                                 uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmWo,
                const __grid_constant__ CUtensorMap tmW1_3, const __grid_constant__ CUtensorMap tmW2, const TailParams p) {

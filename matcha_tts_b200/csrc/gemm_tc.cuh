@@ -105,12 +105,15 @@ struct GemmParams {
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
 };
 
-template <int BN, int EPI = EPI_PLAIN>
+// KSUB = number of 64-column K chunks per pipeline stage.  KSUB = 2 needs the 3-D tensor maps ([nk][rows][64]
+// views, box {64, 128, 2}): one 32 KB TMA instruction per operand and stage -- a cp.async.bulk.tensor costs its
+// issuing thread ~330 cycles whatever the box size, which would cap the 256-cycle stage of a 128-wide N tile.
+template <int BN, int EPI = EPI_PLAIN, int KSUB = 1>
 struct GemmSmem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2 * KSUB;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2 * KSUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (KSUB == 2 ? 3 : 6);
   // per-column epilogue parameters of ALL n-tiles, staged once per CTA: [bias | p1 | p2] x PAR_N
   static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : 1024;  // max N of one launch
   static constexpr int PAR_BYTES = ((EPI == EPI_SNAKE || EPI == EPI_LN) ? 3 : 1) * PAR_N * 4;
@@ -170,11 +173,12 @@ __device__ __forceinline__ void epi_resid_add(uint32_t st, int lane, const uint4
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int KSUB = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using SM = GemmSmem<BN, EPI>;
+  using SM = GemmSmem<BN, EPI, KSUB>;
+  static_assert(KSUB == 1 || (KSUB == 2 && BN == 128), "two K chunks per stage only for the 128-wide N tile");
   constexpr int PN = SM::PAR_N;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
@@ -236,13 +240,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint64_t pol = l2_policy_evict_last();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile % p.n_tiles) * BN;
-      for (int kc = 0; kc < total_chunks; ++kc) {
+      for (int kc = 0; kc < total_chunks; kc += KSUB) {
         mbar_wait(&empty_bar[stage], phase ^ 1);   // converged warp; one elected lane issues
         if (elect_one()) {
           uint8_t* sb = smem + stage * SM::STAGE_BYTES + SM::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], SM::B_BYTES);
-          if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
-          else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+          if constexpr (KSUB == 1) {
+            if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
+            else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+          } else {
+            if (p.w_hint) tma_load_3d_hint(sb, &tmB, &full_bar[stage], 0, n0, kc, pol);
+            else tma_load_3d(sb, &tmB, &full_bar[stage], 0, n0, kc);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -250,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
 
-  if (warp == 0 && (int)blockIdx.x < total_tiles && p.a_prefetch) {
+  if (KSUB == 1 && warp == 0 && (int)blockIdx.x < total_tiles && p.a_prefetch) {
     // warm the TLB / L2 path of this CTA's first activation tiles while the previous kernel drains
     if (elect_one()) {
       const int r0 = ((int)blockIdx.x / p.n_tiles) * GEMM_BM;
@@ -276,11 +285,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int s = 0; s < p.num_segs; ++s) {
         const GemmSeg sg = p.seg[s];
         const CUtensorMap* tm = sg.src ? &tmA1 : &tmA0;
-        for (int c = 0; c < sg.nchunks; ++c) {
+        for (int c = 0; c < sg.nchunks; c += KSUB) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], SM::A_BYTES);
-            tma_load_2d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
+            if constexpr (KSUB == 1)
+              tma_load_2d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
+            else
+              tma_load_3d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], 0, r0 + sg.row_shift, sg.col0 / GEMM_BK + c);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -299,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const int rc0 = (EPI == EPI_STATS && p.res_chunk0 > 0) ? p.res_chunk0 : total_chunks;  // dual: both TMEM halves
-      for (int kc = 0; kc < total_chunks; ++kc) {
+      for (int kc = 0; kc < total_chunks; kc += KSUB) {
         const uint32_t d_tmem = tmem_base + ((kc >= rc0) ? BN : as * BN);
         const int kfirst = (kc >= rc0) ? rc0 : 0;
         mbar_wait(&full_bar[stage], phase);
@@ -310,10 +322,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint64_t db = umma_desc_sw128(sa + SM::A_BYTES);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kc - kfirst) | k) != 0);
+          for (int sub = 0; sub < KSUB; ++sub)   // K sub-chunk tiles are consecutive in the stage; descriptor address in 16-B units
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_f16(d_tmem, da + sub * ((GEMM_BM * GEMM_BK * 2) >> 4) + 2 * k, db + sub * ((BN * GEMM_BK * 2) >> 4) + 2 * k, idesc,
+                       ((kc - kfirst) | sub | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (kc == total_chunks - 1) umma_commit(&tfull_bar[as]);
+          if (kc + KSUB >= total_chunks) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

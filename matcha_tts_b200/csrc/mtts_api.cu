@@ -73,10 +73,12 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 
 // fp16 [rows, nk*64] row-major viewed as [nk][rows][64]: one box = nk K-chunks of box_rows x 64, landing in
 // shared memory as nk consecutive 128B-swizzled tiles (a single TMA instruction for a whole operand piece)
-static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t nk, uint64_t pitch, uint32_t box_rows) {
+static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t nk, uint64_t pitch, uint32_t box_rows,
+                     uint32_t box_nk = 0) {
+  if (box_nk == 0) box_nk = nk;
   cuuint64_t dims[3] = {64, rows, nk};
   cuuint64_t strides[2] = {pitch * 2, 128};
-  cuuint32_t box[3] = {64, box_rows, nk};
+  cuuint32_t box[3] = {64, box_rows, box_nk};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -87,6 +89,18 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t n
              (unsigned long long)rows, nk, (unsigned long long)pitch, box_rows);
     return fail(MTTS_ECUDA, buf);
   }
+  return 0;
+}
+
+// An operand with both views: d2 = 2-D [rows, cols] (box 64 x box_rows), d3 = [cols/64][rows][64] with box
+// {64, 128, 2} (two K chunks per TMA instruction; used by the 128-wide-N GEMM variant), when cols % 128 == 0.
+struct TMap {
+  CUtensorMap d2, d3;
+};
+static int make_tmap(TMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+  if (make_map(&m->d2, base, rows, cols, pitch, box_rows)) return MTTS_ECUDA;
+  m->d3 = m->d2;
+  if (cols % 128 == 0 && make_map3(&m->d3, base, rows, (uint32_t)(cols / 64), pitch, 128, 2)) return MTTS_ECUDA;
   return 0;
 }
 
@@ -116,8 +130,8 @@ struct StageW {
   int src_cols[2];  // padded columns of each input source
   size_t c1, c2, qkv, wo, ff1, ff2;  // fp16 weights (byte offsets); c1 also holds res_conv
   size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
-  CUtensorMap m_c1, m_c2, m_qkv, m_wo, m_ff1, m_ff2;
-  CUtensorMap m_c1h, m_c2h;  // same weights, 128-row boxes (BN = 128 tiles)
+  TMap m_c1, m_c2, m_qkv;
+  CUtensorMap m_wo, m_ff1, m_ff2;
   CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 64, 4}: one hidden chunk of the fused tail (ff_tail.cuh)
 };
 
@@ -130,14 +144,15 @@ struct WsLayout {
 };
 
 struct LevelMaps {
-  CUtensorMap h1, a, o, s, q, k, vt;
+  TMap h1, a;
+  CUtensorMap o, s, q, k, vt;
   CUtensorMap o3;  // o as [2][rows][64], box {64, 128, 2} (fused tail)
 };
 struct Plan {
   WsLayout w;
   char* ws;
   LevelMaps lv[2];
-  CUtensorMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
+  TMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
 };
 
 struct GraphKey {
@@ -161,8 +176,7 @@ struct MttsHandle {
   size_t freqs, tw1, tb1, tw2, tb2, mlpW, mlpB;
   size_t w_down0, w_down1, w_up0, w_up1, w_fin, w_proj;
   size_t b_down0, b_down1, b_up0, b_up1, b_fin, gnf_g, gnf_b, b_proj;
-  CUtensorMap m_down0, m_down1, m_up0, m_up1, m_fin, m_proj;
-  CUtensorMap m_down0h, m_down1h, m_up0h, m_up1h, m_finh;  // 128-row boxes
+  TMap m_down0, m_down1, m_up0, m_up1, m_fin, m_proj;
   bool maps_ready = false;
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
@@ -318,27 +332,20 @@ static int build_weight_maps(MttsHandle* h) {
   for (int s = 0; s < 6; ++s) {
     StageW& w = h->st[s];
     const int ci = w.src_cols[0] + w.src_cols[1];
-    if (make_map(&w.m_c1, a + w.c1, C, 4 * ci, 4 * ci, 256)) return MTTS_ECUDA;
-    if (make_map(&w.m_c2, a + w.c2, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-    if (make_map(&w.m_c1h, a + w.c1, C, 4 * ci, 4 * ci, 128)) return MTTS_ECUDA;
-    if (make_map(&w.m_c2h, a + w.c2, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
-    if (make_map(&w.m_qkv, a + w.qkv, 384, C, C, 128)) return MTTS_ECUDA;
+    if (make_tmap(&w.m_c1, a + w.c1, C, 4 * ci, 4 * ci, 256)) return MTTS_ECUDA;
+    if (make_tmap(&w.m_c2, a + w.c2, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+    if (make_tmap(&w.m_qkv, a + w.qkv, 384, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff2, a + w.ff2, C, 4 * C, 4 * C, 256)) return MTTS_ECUDA;
     if (make_map3(&w.t_ff1, a + w.ff1, 4 * C, 4, C, 64)) return MTTS_ECUDA;
   }
-  if (make_map(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-  if (make_map(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-  if (make_map(&h->m_up0, a + h->w_up0, 2 * C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-  if (make_map(&h->m_up1, a + h->w_up1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-  if (make_map(&h->m_fin, a + h->w_fin, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
-  if (make_map(&h->m_proj, a + h->w_proj, 128, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&h->m_down0h, a + h->w_down0, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
-  if (make_map(&h->m_down1h, a + h->w_down1, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
-  if (make_map(&h->m_up0h, a + h->w_up0, 2 * C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
-  if (make_map(&h->m_up1h, a + h->w_up1, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
-  if (make_map(&h->m_finh, a + h->w_fin, C, 3 * C, 3 * C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_up0, a + h->w_up0, 2 * C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_up1, a + h->w_up1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_fin, a + h->w_fin, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
+  if (make_tmap(&h->m_proj, a + h->w_proj, 128, C, C, 128)) return MTTS_ECUDA;
   h->maps_ready = true;
   return 0;
 }
@@ -398,8 +405,8 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
     const uint64_t rows = lv ? w.rowsH : w.rowsT;
     const int Lpad = lv ? w.LpadH : w.LpadT;
     LevelMaps& m = P.lv[lv];
-    if (make_map(&m.h1, b + w.h1, rows, C, C, 128)) return MTTS_ECUDA;
-    if (make_map(&m.a, b + w.a, rows, C, C, 128)) return MTTS_ECUDA;
+    if (make_tmap(&m.h1, b + w.h1, rows, C, C, 128)) return MTTS_ECUDA;
+    if (make_tmap(&m.a, b + w.a, rows, C, C, 128)) return MTTS_ECUDA;
     if (make_map(&m.o, b + w.o, rows, 128, 128, 128)) return MTTS_ECUDA;
     if (make_map3(&m.o3, b + w.o, rows, 2, 128, 128)) return MTTS_ECUDA;
     if (make_map(&m.s, b + w.s, rows, 4 * C, 4 * C, 128)) return MTTS_ECUDA;
@@ -408,18 +415,18 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
     if (make_map(&m.vt, b + w.vt, (uint64_t)B * 128, Lpad, Lpad, 64)) return MTTS_ECUDA;
   }
   const uint64_t rT = w.rowsT, rH = w.rowsH;
-  if (make_map(&P.x0, b + w.x0, rT, w.cinp, w.cinp, 128)) return MTTS_ECUDA;
-  if (make_map(&P.skip0, b + w.skip0, rT, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.skip0_pair, b + w.skip0, rH, 2 * C, 2 * C, 128)) return MTTS_ECUDA;  // rows (2m, 2m+1) side by side
-  if (make_map(&P.xD0, b + w.xD0, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.skip1, b + w.skip1, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xD1, b + w.xD1, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xM0, b + w.xM0, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xM1, b + w.xM1, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xU0s, b + w.xU0s, rH, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xU0, b + w.xU0, rT, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xU1s, b + w.xU1s, rT, C, C, 128)) return MTTS_ECUDA;
-  if (make_map(&P.xF, b + w.xF, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.x0, b + w.x0, rT, w.cinp, w.cinp, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.skip0, b + w.skip0, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.skip0_pair, b + w.skip0, rH, 2 * C, 2 * C, 128)) return MTTS_ECUDA;  // rows (2m, 2m+1) side by side
+  if (make_tmap(&P.xD0, b + w.xD0, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.skip1, b + w.skip1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xD1, b + w.xD1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xM0, b + w.xM0, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xM1, b + w.xM1, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xU0s, b + w.xU0s, rH, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xU0, b + w.xU0, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xU1s, b + w.xU1s, rT, C, C, 128)) return MTTS_ECUDA;
+  if (make_tmap(&P.xF, b + w.xF, rT, C, C, 128)) return MTTS_ECUDA;
   CUDA_TRY(cudaMemsetAsync(ws, 0, w.total, stream));
   auto res = h->plans.emplace(key, P);
   *out = &res.first->second;
@@ -467,16 +474,16 @@ static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 gr
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int KSUB = 1>
 static int set_gemm_attr() {
-  CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN, EPI>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN, EPI, KSUB>::TOTAL));
   return 0;
 }
 
-template <int BN, int EPI>
-static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
-                       const GemmParams& p, cudaStream_t stream, double aflops = 0.0) {
+template <int BN, int EPI, int KSUB>
+static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
+                            const GemmParams& p, cudaStream_t stream, double aflops) {
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
@@ -485,9 +492,23 @@ static int launch_gemm(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& 
   pp.w_hint = h->w_hint ? 1 : 0;
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
-  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI>::TOTAL, stream, a0, a1, wmap, pp));
+  CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
+                    wmap, pp));
   launched(h);
   return 0;
+}
+
+// 256-wide N tiles use the 2-D maps (one 64-column K chunk per stage), 128-wide ones the 3-D maps (two chunks)
+template <int BN, int EPI>
+static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap& wmap, const GemmParams& p,
+                       cudaStream_t stream, double aflops = 0.0) {
+  if constexpr (BN == 128) {
+    for (int i = 0; i < p.num_segs; ++i)
+      if ((p.seg[i].nchunks & 1) || ((p.seg[i].col0 / 64) & 1)) return fail(MTTS_EINVAL, "128-wide N tile needs whole 128-column K pairs");
+    return launch_gemm_maps<128, EPI, 2>(h, a0.d3, a1.d3, wmap.d3, p, stream, aflops);
+  } else {
+    return launch_gemm_maps<BN, EPI, 1>(h, a0.d2, a1.d2, wmap.d2, p, stream, aflops);
+  }
 }
 
 static void segs_taps(GemmParams& p, int ntaps, const int* shifts, int cols0, int cols1) {
@@ -508,7 +529,7 @@ struct LevelCtx {
 };
 
 // One resnet + transformer stage (reference ResnetBlock1D :785-790 + BasicTransformerBlock :733-744).
-static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CUtensorMap& in0, const CUtensorMap& in1,
+static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TMap& in0, const TMap& in1,
                      __half* out, int t_off, int t_stride, cudaStream_t stream) {
   const WsLayout& w = P.w;
   const StageW& sw = h->st[s];
@@ -539,7 +560,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
     p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
     p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1h, p, stream, fr * C * 4 * ci_real)) return e; }
+    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
   }
   const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
@@ -556,7 +577,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2h, p, stream, fr * C * 3 * C)) return e; }
+    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
   }
   // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
@@ -604,21 +625,21 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const CU
     segs_taps(p, 1, kTap1, 128, 0);
     p.n_tiles = 1; p.bias = F(sw.o_b); p.resid = H(w.xr); p.out = H(w.xa);
     p.ln_g = F(sw.ln3_g); p.ln_b = F(sw.ln3_b); p.out2 = H(w.a);
-    if (int e = launch_gemm<256, EPI_LN>(h, lm.o, lm.o, sw.m_wo, p, stream, fr * C * 128)) return e;
+    if (int e = launch_gemm_maps<256, EPI_LN, 1>(h, lm.o, lm.o, sw.m_wo, p, stream, fr * C * 128)) return e;
   }
   // s = SnakeBeta(c W1^T + b1)
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
     p.n_tiles = 4; p.bias = F(sw.ff1_b); p.sn_a = F(sw.sn_a); p.sn_ib = F(sw.sn_ib); p.out = H(w.s); p.ldo = 4 * C;
-    if (int e = launch_gemm<256, EPI_SNAKE>(h, lm.a, lm.a, sw.m_ff1, p, stream, fr * 4 * C * C)) return e;
+    if (int e = launch_gemm_maps<256, EPI_SNAKE, 1>(h, lm.a.d2, lm.a.d2, sw.m_ff1, p, stream, fr * 4 * C * C)) return e;
   }
   // out = (x_a + s W2^T + b2) * m      (every consumer of a stage output masks it first)
   {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, 4 * C, 0);
     p.n_tiles = 1; p.bias = F(sw.ff2_b); p.resid = H(w.xa); p.rowmask = lc.mask; p.out = out;
-    if (int e = launch_gemm<256, EPI_PLAIN>(h, lm.s, lm.s, sw.m_ff2, p, stream, fr * C * 4 * C)) return e;
+    if (int e = launch_gemm_maps<256, EPI_PLAIN, 1>(h, lm.s, lm.s, sw.m_ff2, p, stream, fr * C * 4 * C)) return e;
   }
   return 0;
 }
@@ -640,8 +661,8 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
               reinterpret_cast<const int*>(ws + w.rowbH), reinterpret_cast<const int*>(ws + w.npadH)};
   float* part = reinterpret_cast<float*>(ws + w.part);
 
-  auto level_conv = [&](const CUtensorMap& in, const CUtensorMap& wmap, const CUtensorMap& wmaph, size_t bias,
-                        const LevelCtx& lc, __half* out, int mode) -> int {
+  auto level_conv = [&](const TMap& in, const TMap& wmap, size_t bias, const LevelCtx& lc, __half* out,
+                        int mode) -> int {
     GemmParams p{};
     p.rowb = lc.rowb; p.Lp = lc.Lp; p.ldr = C; p.bias = F(bias); p.out = out; p.rowmask = lc.mask;
     p.mask_mul = 1; p.mask_nstep = 0; p.ldo = C; p.n_tiles = 1; p.M = lc.rows;
@@ -658,16 +679,16 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     }
     // k3 convs: out rows * 256 * 768; ConvTranspose: B*H input rows * 512 outputs * 512 (two 2-tap phases)
     const double af = (mode == 2) ? 2.0 * w.B * (double)w.H * 512 * 512 : 2.0 * w.B * (double)lc.L * C * 3 * C;
-    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmaph, p, stream, af); }
+    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmap, p, stream, af); }
     return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream, af);
   };
 
   // down 0 @T
   if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip0_pair, h->m_down0, h->m_down0h, h->b_down0, lH, H(w.xD0), 1)) return e;
+  if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
   // down 1 @T/2
   if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip1, h->m_down1, h->m_down1h, h->b_down1, lH, H(w.xD1), 0)) return e;
+  if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
   // mid
   if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
   if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
@@ -675,18 +696,18 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
   if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
   {
     LevelCtx lc = lT;  // mask of the OUTPUT rows (level T), indexed 2*r + phase
-    if (int e = level_conv(P.xU0s, h->m_up0, h->m_up0h, h->b_up0, lc, H(w.xU0), 2)) return e;
+    if (int e = level_conv(P.xU0s, h->m_up0, h->b_up0, lc, H(w.xU0), 2)) return e;
   }
   // up 1 @T : cat[x, skip0]
   if (int e = run_stage(h, P, 5, lT, P.xU0, P.skip0, H(w.xU1s), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.xU1s, h->m_up1, h->m_up1h, h->b_up1, lT, H(w.xF), 0)) return e;
+  if (int e = level_conv(P.xU1s, h->m_up1, h->b_up1, lT, H(w.xF), 0)) return e;
   // final block + projection + ODE update
   {
     GemmParams p{};
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(h->b_fin); p.out = H(w.y);
-    if (h->conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_finh, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
+    if (h->conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
@@ -825,7 +846,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   MttsHandle* h = new MttsHandle();
   h->cfg = *cfg;
   h->device = device;
-  h->cinp = (int)align_up(cfg->in_channels, 64);
+  h->cinp = (int)align_up(cfg->in_channels, 128);  // whole 128-column K pairs for the 3-D TMA boxes
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
@@ -851,8 +872,8 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     h->num_sms = prop.multiProcessorCount;
     int e = 0;
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
-    e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV>(); e |= set_gemm_attr<128, EPI_FINAL>();
-    e |= set_gemm_attr<128, EPI_PLAIN>(); e |= set_gemm_attr<128, EPI_STATS>();
+    e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
+    e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
@@ -1137,11 +1158,16 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
   if (N % 256 == 0) {
     if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 256)) return MTTS_ECUDA;
     p.n_tiles = N / 256;
-    e = launch_gemm<256, EPI_PLAIN>(h, ma, ma, mw, p, stream);
+    e = launch_gemm_maps<256, EPI_PLAIN, 1>(h, ma, ma, mw, p, stream, 0.0);
+  } else if (C % 128 == 0) {   // production 128-wide path: two K chunks per stage through the 3-D maps
+    TMap ta, tw;
+    if (make_tmap(&ta, A, rows, C, C, 128) || make_tmap(&tw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;
+    p.n_tiles = N / 128;
+    e = launch_gemm<128, EPI_PLAIN>(h, ta, ta, tw, p, stream);
   } else {
     if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;
     p.n_tiles = N / 128;
-    e = launch_gemm<128, EPI_PLAIN>(h, ma, ma, mw, p, stream);
+    e = launch_gemm_maps<128, EPI_PLAIN, 1>(h, ma, ma, mw, p, stream, 0.0);
   }
   h->launch_limit = saved;
   return e;

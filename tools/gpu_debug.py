@@ -74,7 +74,7 @@ def main():
 
     # prologue
     run(6)
-    x0 = buf("x0", T, LpT, 192)
+    x0 = buf("x0", T, LpT, 256)
     xin = torch.cat([z0, mu], 1) * mask
     cmp("x0", x0[:, :160], xin)
     te6 = U.ws_tensor(eng, B, T, "te6", B, 1536, torch.float32)
