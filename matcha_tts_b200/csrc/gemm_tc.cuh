@@ -42,7 +42,9 @@ namespace mtts {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_NCG = 2;                                   // epilogue column groups per TMEM lane quarter (4 = 16 warps was
+                                                              // measured: no faster per tile, and it costs a pipeline stage)
+constexpr int GEMM_EPI_WARPS = 4 * GEMM_NCG;                  // 8
 constexpr int GEMM_THREADS = 96 + 32 * GEMM_EPI_WARPS;        // 352: A producer, MMA, B producer, 8 epilogue warps
 constexpr int GEMM_MAX_SEGS = 9;
 constexpr int GEMM_STAGING_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 32 fp16, swizzled
@@ -113,13 +115,13 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2 * KSUB;
   static constexpr int B_BYTES = BN * GEMM_BK * 2 * KSUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (KSUB == 2 ? 3 : 6);
+  static constexpr int STAGES = (BN == 256) ? 4 : (KSUB == 2 ? 3 : 4);
   // per-column epilogue parameters of ALL n-tiles, staged once per CTA: [bias | p1 | p2] x PAR_N
-  static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : 1024;  // max N of one launch
+  static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : (BN == 128 ? 512 : 1024);  // max N of one launch
   static constexpr int PAR_BYTES = ((EPI == EPI_SNAKE || EPI == EPI_LN) ? 3 : 1) * PAR_N * 4;
-  static constexpr int RED_BYTES = 2 * GEMM_BM * 2 * 8;  // LayerNorm partial (sum, sumsq) per row and column half, x2 buffers
-  static constexpr int TOTAL = 1024 /*align slack*/ + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_BYTES +
-                               PAR_BYTES + RED_BYTES + 256;
+  static constexpr int RED_BYTES = (EPI == EPI_LN) ? 2 * GEMM_BM * GEMM_NCG * 8 : 0;  // LayerNorm partials per row and column group, x2
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_BYTES + PAR_BYTES + RED_BYTES + 256;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
 };
 
 // ---- epilogue helpers -------------------------------------------------------------------------
@@ -171,7 +173,7 @@ __device__ __forceinline__ void epi_resid_add(uint32_t st, int lane, const uint4
   // the __syncwarp()s inside epi_store_h32
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory"); }
 
 template <int BN, int EPI, int KSUB = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -184,8 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "BN must be 128 or 256");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need 1024-byte aligned bases
   uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;
   float* s_par = reinterpret_cast<float*>(staging + GEMM_EPI_WARPS * GEMM_STAGING_BYTES);
   uint8_t* s_red = reinterpret_cast<uint8_t*>(s_par) + SM::PAR_BYTES;
@@ -339,11 +341,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= 3) {
     // ===================================== epilogue =========================================
-    constexpr int CW = BN / 2;    // columns per epilogue warp
+    constexpr int CW = BN / GEMM_NCG;  // columns per epilogue warp
     constexpr int NCH = CW / 32;  // 32-column chunks per warp
     const int ew = warp - 3;
     const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int hcol = ew >> 2;     // which half of the tile's columns
+    const int hcol = ew >> 2;     // which column group of the tile
     const int cbase = hcol * CW;
     const uint32_t st = smem_u32(staging + ew * GEMM_STAGING_BYTES);
     const uint32_t spar = smem_u32(s_par);
@@ -385,6 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int c = 0; c < NCH; ++c) {
           float* v = vbuf[c & 1];
           tmem_ld_wait();
+          if (tl && ew == 0 && lane == 0 && c == 0 && tile == (int)blockIdx.x) tl[11] = clock64();
           if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -423,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }
           epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
+          if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[12 + (c != 0)] = clock64();
         }
         if constexpr (EPI == EPI_STATS) {
           // deterministic per-(utterance, group) partial sums of this warp's 32 rows x 4 groups:
@@ -469,6 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __syncwarp();
           }
         }
+        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[14] = clock64();
         if constexpr (EPI == EPI_STATS) {
           if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
             __half* rob = p.res_out + (size_t)rw0 * p.ldo + n0 + cbase;
@@ -489,17 +494,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if constexpr (EPI == EPI_LN) {
           // LayerNorm over the full BN-wide row: combine the two column halves through smem
-          const uint32_t red = smem_u32(s_red) + (as ? GEMM_BM * 16 : 0);  // double-buffered by accumulator stage
+          const uint32_t red = smem_u32(s_red) + (as ? GEMM_BM * GEMM_NCG * 8 : 0);  // double-buffered by accumulator stage
           const int trow = q * 32 + lane;
-          sts_f32(red + (trow * 2 + hcol) * 8, lsum);
-          sts_f32(red + (trow * 2 + hcol) * 8 + 4, lsq);
+          sts_f32(red + (trow * GEMM_NCG + hcol) * 8, lsum);
+          sts_f32(red + (trow * GEMM_NCG + hcol) * 8 + 4, lsq);
           tmem_st_wait();
           epi_bar_sync();
-          const float osum = lds_f32(red + (trow * 2 + (hcol ^ 1)) * 8);
-          const float osq = lds_f32(red + (trow * 2 + (hcol ^ 1)) * 8 + 4);
-          // add in a fixed (half 0, half 1) order so both warps of a pair see bit-identical statistics
-          const float tsum = hcol ? (osum + lsum) : (lsum + osum);
-          const float tsq = hcol ? (osq + lsq) : (lsq + osq);
+          // sum the column groups in a fixed order so every warp of a row sees bit-identical statistics
+          float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+          for (int g = 0; g < GEMM_NCG; ++g) {
+            tsum += lds_f32(red + (trow * GEMM_NCG + g) * 8);
+            tsq += lds_f32(red + (trow * GEMM_NCG + g) * 8 + 4);
+          }
           const float mean = tsum * (1.f / BN);
           const float var = fmaxf(tsq * (1.f / BN) - mean * mean, 0.f);
           const float rstd = rsqrtf(var + 1e-5f);

@@ -1145,7 +1145,7 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
 int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
                     int ntaps, const int* shifts, void* stream_) {
   if (!h || !A || !W || !out) return fail(MTTS_EINVAL, "null argument");
-  if (C % 64 || N % 128 || N > 1024 || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
+  if (C % 64 || N % 128 || N > 1024 || (N % 256 && N > 512) || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
   if (int e = init_encode()) return e;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUtensorMap ma, mw;

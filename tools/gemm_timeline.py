@@ -62,7 +62,8 @@ def main():
         span = float(a[:, 10].max() - a[:, 8].min()) / 1e3
         first_wait = float(a[:, 9].min())
         gap = "" if prev_exit is None else f"{(first_wait - prev_exit) / 1e3:7.2f} (since prev GEMM's last exit)"
-        lines.append(f"{lab:16s} {n:5d} {us(1):6.2f} {us(2):8.2f} {us(3):7.2f} {us(4):10.2f} {us(5):10.2f} {us(6):9.2f} {us(7):6.2f} | {span:7.2f}  {gap}   clk={ghz:.2f}GHz")
+        lines.append(f"{lab:16s} {n:5d} {us(1):6.2f} {us(2):8.2f} {us(3):7.2f} {us(4):10.2f} {us(5):10.2f} {us(6):9.2f} {us(7):6.2f} | {span:7.2f}  {gap}   clk={ghz:.2f}GHz"
+                     f"   epi: ld0 {us(11):.2f} chunk0 {us(12):.2f} lastchunk {us(13):.2f} stats {us(14):.2f}")
         prev_exit = float(a[:, 10].max())
     txt = "\n".join(lines)
     print(txt)
