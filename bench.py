@@ -97,7 +97,7 @@ def cpu_reference(B, T, n_timesteps, steps, warmup, budget_s):
         t0 = time.perf_counter()
         O.euler_solve(sd, cfg, z0, mu, mask, n_timesteps)
         t_row = time.perf_counter() - t0
-    rows = int(max(1, min(8, B, budget_s / max(1, steps + warmup) / t_row)))
+    rows = int(max(1, min(16, B, budget_s / max(1, steps + warmup) / t_row)))
     mu, mask, z0, _ = O.make_inputs(cfg, rows, T, None, seed=1)
     times = []
     with torch.inference_mode():

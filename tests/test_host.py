@@ -160,3 +160,20 @@ def test_matcha_facade_signature():
     assert keys[0] == "mel_mean" and keys[1] == "mel_std" and keys[2].startswith("decoder.estimator.time_mlp")
     with pytest.raises(RuntimeError):
         m.synthesize(torch.zeros(1, 4, dtype=torch.long), torch.tensor([4]), 2)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU port of the reference path) on a tiny shape: one JSON line with the
+    contract's keys, and nothing else on stdout."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--batch", "2", "--frames", "32", "--n-timesteps", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "mel-frames/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
