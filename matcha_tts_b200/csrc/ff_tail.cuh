@@ -12,16 +12,17 @@
 //         cols [384,512) Cc : c = LayerNorm3(x_a) as packed fp16 pairs -- the A operand of FF1 is read from TENSOR
 //                             MEMORY (an N=64 MMA reading a 4 KB A tile from shared memory every 32 cycles would be
 //                             shared-memory-bandwidth bound)
-//   SMEM  S  2x16 KB : s chunk j (128x64 fp16) double-buffered (A operand of FF2)
-//         ring 5x32 KB : TMA-fed operand pieces, ONE cp.async.bulk.tensor each -- an issue costs the thread
+//   SMEM  S  3x16 KB : s chunk j (128x64 fp16), three buffers (A operand of FF2)
+//         ring 4x32 KB : TMA-fed operand pieces, ONE cp.async.bulk.tensor each -- an issue costs the thread
 //                        ~330 cycles whatever the box size (profiles/r01_tma_issue_microbench.txt), so pieces
 //                        are as large as a 512-cycle MMA group needs:
 //                          o  tile    box {64, 128 rows, 2 K-chunks} of o  viewed as [2][rows][64]
 //                          Wo K-chunk box {64, 256 rows}                 (B operand, N = 256)
 //                          W1 chunk j box {64, 64 rows, 4 K-chunks}  of W1 viewed as [4][1024][64] (N = 64, K = 256)
 //                          W2 chunk j box {64, 256 rows}                 (B operand, N = 256, K = 64)
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogue (four column groups per TMEM lane
-// quarter = four warps per scheduler: the SnakeBeta epilogue is latency-bound with fewer).  The MMA stream is software-pipelined over the 16 hidden chunks
+// Warp roles: warp 0 TMA producer, warp 1 issues to_out + FF1, warp 2 issues FF2 (two issuers: the tcgen05 queue is
+// short, so every barrier wait / commit of a single issuer idles the tensor pipe), warps 3-18 epilogue (four column
+// groups per TMEM lane quarter).  The MMA stream is software-pipelined over the 16 hidden chunks
 //   FF1_0 FF1_1 | FF2_0 FF1_2 | FF2_1 FF1_3 | ... | FF2_14 | FF2_15
 // so that the tensor pipe works on FF2_{j-1} and FF1_{j+1} while the epilogue warps apply SnakeBeta to chunk j.
 #pragma once
@@ -48,14 +49,15 @@ struct TailParams {
   long long* tl;         // debug timeline [gridDim.x][128] clock64 stamps of the first tile (null in production)
 };
 
-constexpr int TAIL_NST = 5;
+constexpr int TAIL_NST = 4;
 constexpr int TAIL_PIECE = 32768;
+constexpr int TAIL_NSB = 3;                                           // s chunk buffers (FF1 runs two chunks ahead of FF2)
 constexpr int TAIL_NJ = 16;                                           // hidden chunks of 64
 constexpr int TAIL_NCG = 4;                                           // column groups -> 16 epilogue warps (4 per scheduler)
-constexpr int TAIL_THREADS = 64 + 128 * TAIL_NCG;
-constexpr int TAIL_OFF_S = 0;                                         // 2 x 16 KB
-constexpr int TAIL_OFF_RING = TAIL_OFF_S + 2 * 16384;                 // 32768
-constexpr int TAIL_OFF_PAR = TAIL_OFF_RING + TAIL_NST * TAIL_PIECE;   // 196608
+constexpr int TAIL_THREADS = 96 + 128 * TAIL_NCG;                      // producer, two MMA issuers, 16 epilogue warps
+constexpr int TAIL_OFF_S = 0;                                         // 3 x 16 KB
+constexpr int TAIL_OFF_RING = TAIL_OFF_S + TAIL_NSB * 16384;          // 49152
+constexpr int TAIL_OFF_PAR = TAIL_OFF_RING + TAIL_NST * TAIL_PIECE;   // 180224
 constexpr int TAIL_PAR_FLOATS = 4 * 256 + 3 * 1024;                   // b_o ln_g ln_b b2 | b1 sn_a sn_ib
 // epilogue staging (16 warps x 32 rows x 64 B = 32 KB) aliases the S buffers: it is only used at the start (E1)
 // and at the end (E3) of a tile, when no FF2 MMA can be reading S (r_full / r_done imply all MMAs retired)
@@ -84,12 +86,12 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   uint64_t* c_ready = r_full + 1;                   // c written to TMEM, x_a written back to TMEM
   uint64_t* d1_full = r_full + 2;                   // [2] FF1 chunk accumulator complete
   uint64_t* d1_empty = r_full + 4;                  // [2] epilogue has read the FF1 chunk accumulator
-  uint64_t* s_ready = r_full + 6;                   // [2] s chunk written to smem
-  uint64_t* s_empty = r_full + 8;                   // [2] FF2 has consumed the s chunk
-  uint64_t* r_done = r_full + 10;                   // all FF2 MMAs of the tile complete
-  uint64_t* r_empty = r_full + 11;                  // epilogue has read the final accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 12);
-  static_assert((2 * TAIL_NST + 13) * 8 <= 256, "barrier block");
+  uint64_t* s_ready = r_full + 6;                   // [3] s chunk written to smem
+  uint64_t* s_empty = r_full + 9;                   // [3] FF2 has consumed the s chunk
+  uint64_t* r_done = r_full + 12;                   // all FF2 MMAs of the tile complete
+  uint64_t* r_empty = r_full + 13;                  // epilogue has read the final accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 14);
+  static_assert((2 * TAIL_NST + 15) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -98,20 +100,18 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAIL_NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(r_full, 1); mbar_init(c_ready, NEW);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NEW);
-      mbar_init(&s_ready[i], NEW); mbar_init(&s_empty[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NEW); }
+    for (int i = 0; i < TAIL_NSB; ++i) { mbar_init(&s_ready[i], NEW); mbar_init(&s_empty[i], 1); }
     mbar_init(r_done, 1); mbar_init(r_empty, NEW);
     fence_mbar_init();
     tma_prefetch_desc(&tmO3); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1_3); tma_prefetch_desc(&tmW2);
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  if (warp >= 2) {  // weights-only parameters: staged while the previous kernel drains
-    for (int i = threadIdx.x - 64; i < 256; i += 32 * NEW) {
+  if (warp >= 3) {  // weights-only parameters: staged while the previous kernel drains
+    for (int i = threadIdx.x - 96; i < 256; i += 32 * NEW) {
       s_par[i] = p.b_o[i]; s_par[256 + i] = p.ln_g[i]; s_par[512 + i] = p.ln_b[i]; s_par[768 + i] = p.b2[i];
     }
-    for (int i = threadIdx.x - 64; i < 1024; i += 32 * NEW) {
+    for (int i = threadIdx.x - 96; i < 1024; i += 32 * NEW) {
       s_par[1024 + i] = p.b1[i]; s_par[2048 + i] = p.sn_a[i]; s_par[3072 + i] = p.sn_ib[i];
     }
   }
@@ -167,37 +167,43 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           __syncwarp();
         }
         put_w1(0);
+        put_w1(1);
         for (int j = 0; j < TAIL_NJ; ++j) {
-          if (j + 1 < TAIL_NJ) put_w1(j + 1);
+          if (j + 2 < TAIL_NJ) put_w1(j + 2);
           put2(&tmW2, j * 64, 0);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    // The whole warp runs this code converged (addresses and descriptors stay in uniform registers);
-    // only the tcgen05 instructions themselves are issued by one elected lane.
-    {
-      constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
-      constexpr uint32_t idesc64 = umma_idesc_f16(128, 64);
-      const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
-      const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
-      uint32_t it = 0;  // ring item counter (same sequence as the producer)
-      uint32_t n_tile = 0, n_d1e0 = 0, n_d1e1 = 0, n_sr0 = 0, n_sr1 = 0;
-      auto slot_wait = [&](uint32_t item) -> uint32_t {
-        const uint32_t slot = item % TAIL_NST, use = item / TAIL_NST;
-        mbar_wait(&full_bar[slot], use & 1);
-        tc_fence_after();
-        return ring + slot * TAIL_PIECE;
-      };
-      long long* tl = (p.tl != nullptr) ? p.tl + (size_t)blockIdx.x * 128 : nullptr;
+  } else if (warp == 1 || warp == 2) {
+    // ===================================== MMA issuers ======================================
+    // Converged warps (addresses and descriptors stay in uniform registers); only the tcgen05 instructions are
+    // issued by one elected lane.  Warp 1 owns the to_out + FF1 stream (accumulators R then D1), warp 2 the FF2
+    // stream (accumulates into R); both walk the same ring-item numbering as the producer.
+    constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
+    constexpr uint32_t idesc64 = umma_idesc_f16(128, 64);
+    const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
+    const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
+    auto slot_wait = [&](uint32_t item) -> uint32_t {
+      const uint32_t slot = item % TAIL_NST, use = item / TAIL_NST;
+      mbar_wait(&full_bar[slot], use & 1);
+      tc_fence_after();
+      return ring + slot * TAIL_PIECE;
+    };
+    // ring items of one tile: 0,1 Wo K-chunks | 2 o | W1_0, W1_1 | then (W1_{j+2}, W2_j) for j = 0..15
+    auto item_w1 = [](int k) -> uint32_t { return k < 2 ? 3u + k : 2u * k + 1u; };
+    auto item_w2 = [](int j) -> uint32_t { return j <= 13 ? 6u + 2u * j : 19u + j; };
+    constexpr uint32_t ITEMS = 35;
+    long long* tl = (p.tl != nullptr) ? p.tl + (size_t)blockIdx.x * 128 : nullptr;
+    uint32_t n_tile = 0;
+    if (warp == 1) {
+      uint32_t n_d1e0 = 0, n_d1e1 = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
         if (n_tile != 0) tl = nullptr;
-        // ---- to_out: R = o Wo^T ; ring items: base+0, base+1 = Wo K-chunks, base+2 = o (both K-chunks)
+        const uint32_t base = n_tile * ITEMS;
+        // ---- to_out: R = o Wo^T
         mbar_wait(r_empty, (n_tile & 1) ^ 1);
         tc_fence_after();
         if (tl && lane == 0) tl[0] = clock64();
-        const uint32_t base = it;
         {
           const uint32_t a = slot_wait(base + 2);
           for (int k = 0; k < 2; ++k) {
@@ -213,68 +219,64 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           }
         }
         if (tl && lane == 0) tl[1] = clock64();
-        it = base + 3;
-        // ---- feed-forward
+        // ---- FF1 chunks (A = c from tensor memory)
         mbar_wait(c_ready, n_tile & 1);
         tc_fence_after();
         if (tl && lane == 0) tl[2] = clock64();
-        auto ff1 = [&](int j) {
+        for (int j = 0; j < TAIL_NJ; ++j) {
           const int b = j & 1;
           uint32_t& n = b ? n_d1e1 : n_d1e0;
           mbar_wait(&d1_empty[b], (n & 1) ^ 1);
           ++n;
           tc_fence_after();
           if (tl && lane == 0 && j < 8) tl[4 + 4 * j] = clock64();
-          const uint32_t w = slot_wait(it);
+          const uint32_t item = base + item_w1(j);
+          const uint32_t w = slot_wait(item);
           const uint64_t db0 = umma_desc_sw128(w);
           if (elect_one()) {
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B descriptor address in 16-byte units
-#ifdef TAIL_DEBUG_NO_TS
-                umma_f16(tD1 + b * 64, db0 + 2 * kk, db0 + kc * (8192 >> 4) + 2 * kk, idesc64, (kc | kk) != 0);
-#else
                 umma_f16_ts(tD1 + b * 64, tC + kc * 32 + kk * 8, db0 + kc * (8192 >> 4) + 2 * kk, idesc64, (kc | kk) != 0);
-#endif
-            umma_commit(&empty_bar[it % TAIL_NST]);
+            umma_commit(&empty_bar[item % TAIL_NST]);
             umma_commit(&d1_full[b]);
           }
           __syncwarp();
-          ++it;
           if (tl && lane == 0 && j < 8) tl[5 + 4 * j] = clock64();
-        };
-        auto ff2 = [&](int j) {
-          const int b = j & 1;
-          uint32_t& n = b ? n_sr1 : n_sr0;
-          mbar_wait(&s_ready[b], n & 1);
-          ++n;
+        }
+      }
+    } else {
+      uint32_t n_sr = 0;   // FF2 chunks consumed so far (buffer = n % 3, use = n / 3)
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+        if (n_tile != 0) tl = nullptr;
+        const uint32_t base = n_tile * ITEMS;
+        mbar_wait(c_ready, n_tile & 1);   // x_a is in R
+        tc_fence_after();
+        for (int j = 0; j < TAIL_NJ; ++j) {
+          const uint32_t b = n_sr % TAIL_NSB;
+          mbar_wait(&s_ready[b], (n_sr / TAIL_NSB) & 1);
+          ++n_sr;
           tc_fence_after();
           if (tl && lane == 0 && j < 8) tl[6 + 4 * j] = clock64();
-          const uint32_t w = slot_wait(it);
+          const uint32_t item = base + item_w2(j);
+          const uint32_t w = slot_wait(item);
           const uint64_t da = umma_desc_sw128(sbuf + b * 16384), db = umma_desc_sw128(w);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
-            umma_commit(&empty_bar[it % TAIL_NST]);
+            umma_commit(&empty_bar[item % TAIL_NST]);
             umma_commit(&s_empty[b]);
+            if (j == TAIL_NJ - 1) umma_commit(r_done);
           }
           __syncwarp();
-          ++it;
           if (tl && lane == 0 && j < 8) tl[7 + 4 * j] = clock64();
-        };
-        ff1(0);
-        for (int j = 0; j < TAIL_NJ; ++j) {
-          if (j + 1 < TAIL_NJ) ff1(j + 1);
-          ff2(j);
         }
-        if (elect_one()) umma_commit(r_done);
-        __syncwarp();
       }
     }
   } else {
     // ===================================== epilogue =========================================
-    const int ew = warp - 2;
+    const int ew = warp - 3;
     const int q = warp & 3;     // TMEM lane quarter
     const int cg = ew >> 2;     // column group
     const uint32_t st = smem_u32(smem + TAIL_OFF_STAGING + ew * GEMM_STAGING_BYTES);
@@ -283,7 +285,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const int trow = q * 32 + lane;  // row inside the tile
-    uint32_t n_tile = 0, n_d1f[2] = {0, 0}, n_se[2] = {0, 0};
+    uint32_t n_tile = 0, n_d1f[2] = {0, 0}, n_s = 0;   // n_s: s chunks produced so far (buffer = n % 3, use = n / 3)
     long long* tl = (p.tl != nullptr && ew == 0 && lane == 0) ? p.tl + (size_t)blockIdx.x * 128 + 64 : nullptr;
     pdl_wait();  // x_r / out belong to the dependency chain
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
@@ -360,12 +362,13 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       // ------------------------------------------------ E2: SnakeBeta on the 16 hidden chunks
 #pragma unroll 1
       for (int j = 0; j < TAIL_NJ; ++j) {
-        const int b = j & 1;
+        const int b = j & 1;                 // accumulator buffer
+        const uint32_t sb = n_s % TAIL_NSB;  // s buffer
         if (lane == 0) {
-          mbar_wait(&s_empty[b], (n_se[b] & 1) ^ 1);  // FF2_{j-2} no longer reads S[b]
+          mbar_wait(&s_empty[sb], ((n_s / TAIL_NSB) & 1) ^ 1);  // FF2_{j-3} no longer reads S[sb]
           mbar_wait(&d1_full[b], n_d1f[b] & 1);
         }
-        ++n_se[b];
+        ++n_s;
         ++n_d1f[b];
         __syncwarp();
         tc_fence_after();
@@ -388,7 +391,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           x = v[4 * jj + 2] + b4.z; sn = fast_sin(x * a4.z); v[4 * jj + 2] = fmaf(sn * sn, i4.z, x);
           x = v[4 * jj + 3] + b4.w; sn = fast_sin(x * a4.w); v[4 * jj + 3] = fmaf(sn * sn, i4.w, x);
         }
-        const uint32_t srow = sbuf + b * 16384 + trow * 128;
+        const uint32_t srow = sbuf + sb * 16384 + trow * 128;
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           sts128(srow + (((cg * 2 + u) ^ (trow & 7)) << 4),
@@ -396,7 +399,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
                             pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7])));
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_ready[b]);
+        if (lane == 0) mbar_arrive(&s_ready[sb]);
         if (tl && j < 8) tl[5 + 2 * j] = clock64();
       }
       // ------------------------------------------------ E3: out = (x_a + FF + b2) * mask
