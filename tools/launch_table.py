@@ -15,7 +15,7 @@ def main():
     # the launch list may include weight-packing kernels first; align on the end
     n_per = len(per)
     # take the first complete estimator evaluation: it starts at the first STATS conv GEMM
-    first = next(i for i, nm in enumerate(names) if "gemm_tc_kernel<256, 0>" in nm)
+    first = next(i for i, nm in enumerate(names) if "gemm_tc_kernel<256, 0" in nm)
     last = list(zip(names, ns))[first:first + n_per]
     out = []
     tot = 0.0
