@@ -151,6 +151,7 @@ struct LevelMaps {
 struct Plan {
   WsLayout w;
   char* ws;
+  int te_n = -1, te_solver = -1;  // the solver's time-embedding table in ws.te6 is valid for (n_timesteps, solver)
   LevelMaps lv[2];
   TMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
 };
@@ -725,30 +726,16 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
   return 0;
 }
 
-// masks, row maps, operand buffer, and the time-embedding table for n_t time values in ws.tvals
-static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu, const float* mask, const float* spks,
-                        int n_t, cudaStream_t stream) {
+// The data-independent time path (reference model.py:753-762, :828-832, :780): te6[i][6*256] for the n_t time
+// values in ws.tvals.  Inside a solve it depends only on (weights, n_timesteps, solver), so it is computed once
+// per plan and cached (outside the CUDA graph).
+static int run_time_table(MttsHandle* h, Plan& P, int n_t, cudaStream_t stream) {
   const WsLayout& w = P.w;
   char* ws = P.ws;
   const char* ar = h->arena;
   const int C = h->cfg.channels, Cin = h->cfg.in_channels, TD = 4 * C;
   auto Fw = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto Fa = [&](size_t off) { return reinterpret_cast<const float*>(ar + off); };
-  CUDA_TRY(cudaMemsetAsync(ws + w.vt, 0, w.vt_bytes, stream));
-  if (can_launch(h)) {
-    mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
-                                              reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
-                                              reinterpret_cast<int*>(ws + w.npadH));
-    CUDA_TRY(cudaGetLastError());
-    launched(h);
-  }
-  if (can_launch(h)) {
-    dim3 grid((w.LpT + 31) / 32, w.B);
-    prep_x0_kernel<<<grid, 256, w.cinp * 33 * sizeof(float), stream>>>(
-        x, mu, spks, Fw(w.maskT), w.T, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
-    CUDA_TRY(cudaGetLastError());
-    launched(h);
-  }
   if (can_launch(h)) {
     sinus_emb_kernel<<<(n_t * (Cin / 2) + 255) / 256, 256, 0, stream>>>(Fw(w.tvals), Fa(h->freqs), n_t, Cin / 2, Fw(w.te_e));
     CUDA_TRY(cudaGetLastError());
@@ -767,6 +754,30 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
   if (can_launch(h)) {
     small_linear_kernel<<<(6 * C + 7) / 8, 256, 0, stream>>>(Fw(w.te_h2), Fa(h->mlpW), Fa(h->mlpB), Fw(w.te6), n_t, TD,
                                                               6 * C, 0);
+    CUDA_TRY(cudaGetLastError());
+    launched(h);
+  }
+  return 0;
+}
+
+// masks, row maps and the first conv's operand buffer
+static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu, const float* mask, const float* spks,
+                        cudaStream_t stream) {
+  const WsLayout& w = P.w;
+  char* ws = P.ws;
+  auto Fw = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  // V^T pad columns [L, Lpad) are zeroed once with the whole workspace (get_plan) and never written afterwards
+  if (can_launch(h)) {
+    mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
+                                              reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
+                                              reinterpret_cast<int*>(ws + w.npadH));
+    CUDA_TRY(cudaGetLastError());
+    launched(h);
+  }
+  if (can_launch(h)) {
+    dim3 grid((w.LpT + 31) / 32, w.B);
+    prep_x0_kernel<<<grid, 256, w.cinp * 33 * sizeof(float), stream>>>(
+        x, mu, spks, Fw(w.maskT), w.T, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
     CUDA_TRY(cudaGetLastError());
     launched(h);
   }
@@ -978,21 +989,17 @@ int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const
   if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
   h->launch_count = 0;
   CUDA_TRY(cudaMemcpyAsync(P->ws + P->w.tvals, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream));
-  if (int e = run_prologue(h, *P, x, mu, mask, spks, B, stream)) return e;
+  P->te_n = -1;  // per-utterance times: not a solver table
+  if (int e = run_time_table(h, *P, B, stream)) return e;
+  if (int e = run_prologue(h, *P, x, mu, mask, spks, stream)) return e;
   return run_estimator(h, *P, /*t_off=*/0, /*t_stride=*/1, out, nullptr, 1.f, false, stream);
 }
 
 static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, const float* mask, const float* spks, int n,
                          int solver, cudaStream_t stream) {
   const WsLayout& w = P.w;
-  const int n_t = solver == MTTS_SOLVER_MIDPOINT ? 2 * n : n;
-  if (can_launch(h)) {
-    solver_times_kernel<<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(P.ws + w.tvals), n,
-                                                             solver == MTTS_SOLVER_MIDPOINT);
-    CUDA_TRY(cudaGetLastError());
-    launched(h);
-  }
-  if (int e = run_prologue(h, P, z, mu, mask, spks, n_t, stream)) return e;
+  if (P.te_n != n || P.te_solver != solver) return fail(MTTS_ESTATE, "internal: time-embedding table not prepared");
+  if (int e = run_prologue(h, P, z, mu, mask, spks, stream)) return e;
   const float dt = (float)(1.0 / (double)n);
   float* zmid = reinterpret_cast<float*>(P.ws + w.zmid);
   for (int i = 0; i < n; ++i) {
@@ -1052,12 +1059,26 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
     if (int e = get_plan(h, static_cast<char*>(workspace) + chunks[i].ws_off, avail, chunks[i].nb, T, stream, &plans[i])) return e;
   }
   h->launch_count = 0;
+  for (int i = 0; i < nsub; ++i) {   // time-embedding tables: once per (plan, n_timesteps, solver), outside the graph
+    Plan& P = *plans[i];
+    if (P.te_n == n && P.te_solver == solver) continue;
+    const int n_t = solver == MTTS_SOLVER_MIDPOINT ? 2 * n : n;
+    if (can_launch(h)) {
+      solver_times_kernel<<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(P.ws + P.w.tvals), n,
+                                                               solver == MTTS_SOLVER_MIDPOINT);
+      CUDA_TRY(cudaGetLastError());
+      launched(h);
+    }
+    if (int e = run_time_table(h, P, n_t, stream)) return e;
+    P.te_n = n; P.te_solver = solver;
+  }
   if (!use_graph || debug_mode) return enqueue_solve_chains(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
 
   GraphKey key{z, mu, mask, spks, workspace, B, T, n, solver};
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaGraph_t graph = nullptr;
+    h->launch_count = 0;   // count the kernels inside the graph only (the cached table kernels ran above)
     CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     int e = enqueue_solve_chains(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
     cudaError_t ce = cudaStreamEndCapture(stream, &graph);
