@@ -395,8 +395,8 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           sts128(srow + (((cg * 2 + u) ^ (trow & 7)) << 4),
-                 make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
-                            pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7])));
+                 make_uint4(pack_h2_sat(v[8 * u], v[8 * u + 1]), pack_h2_sat(v[8 * u + 2], v[8 * u + 3]),
+                            pack_h2_sat(v[8 * u + 4], v[8 * u + 5]), pack_h2_sat(v[8 * u + 6], v[8 * u + 7])));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_ready[sb]);

@@ -105,6 +105,8 @@ struct GemmParams {
   long long* tl;
   int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
+  int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
+                   //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
 
 // KSUB = number of 64-column K chunks per pipeline stage.  KSUB = 2 needs the 3-D tensor maps ([nk][rows][64]
@@ -183,7 +185,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   static_assert(KSUB == 1 || (KSUB == 2 && BN == 128), "two K chunks per stage only for the 128-wide N tile");
   constexpr int PN = SM::PAR_N;
   constexpr int STAGES = SM::STAGES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
+  // accumulator stage stride: the STATS variant may feed a second accumulator (res_conv) per tile; with 128-wide tiles
+  // both accumulators of both stages fit (2 x 2 x 128 columns), with 256-wide tiles the dual mode has one stage
+  constexpr uint32_t ACC_STRIDE = (EPI == EPI_STATS && BN == 128) ? 2 * BN : BN;
+  constexpr bool DUAL_DOUBLE = (EPI == EPI_STATS && BN == 128);
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "BN must be 128 or 256");
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -209,6 +215,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   for (int s = 0; s < p.num_segs; ++s) total_chunks += p.seg[s].nchunks;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int total_tiles = m_tiles * p.n_tiles;
+  // i-th tile of this CTA (or -1): round-robin over all tiles, or whole row tiles with their N tiles back to back
+  auto cta_tile = [&](int i) -> int {
+    if (!p.m_major) { const int t = blockIdx.x + i * gridDim.x; return t < total_tiles ? t : -1; }
+    const int mt = blockIdx.x + (i / p.n_tiles) * gridDim.x;
+    return mt < m_tiles ? mt * p.n_tiles + (i % p.n_tiles) : -1;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
@@ -226,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       s_par[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
       if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
-      if constexpr (EPI == EPI_STATS) if (p.res_chunk0 > 0 && i < 256) s_par[512 + i] = p.res_bias[i];
+      if constexpr (EPI == EPI_STATS) if (p.res_chunk0 > 0 && i < 256) s_par[256 + i] = p.res_bias[i];  // the conv's own N is 256
     }
   }
   tc_fence_before();
@@ -240,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     const uint64_t pol = l2_policy_evict_last();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int n0 = (tile % p.n_tiles) * BN;
       for (int kc = 0; kc < total_chunks; kc += KSUB) {
         mbar_wait(&empty_bar[stage], phase ^ 1);   // converged warp; one elected lane issues
@@ -264,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (KSUB == 1 && warp == 0 && (int)blockIdx.x < total_tiles && p.a_prefetch) {
     // warm the TLB / L2 path of this CTA's first activation tiles while the previous kernel drains
     if (elect_one()) {
-      const int r0 = ((int)blockIdx.x / p.n_tiles) * GEMM_BM;
+      const int r0 = (cta_tile(0) / p.n_tiles) * GEMM_BM;
       int kc = 0;
       for (int s = 0; s < p.num_segs && kc < STAGES; ++s) {
         const GemmSeg sg = p.seg[s];
@@ -282,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================================== TMA producer: activations ===========================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int r0 = (tile / p.n_tiles) * GEMM_BM;
       for (int s = 0; s < p.num_segs; ++s) {
         const GemmSeg sg = p.seg[s];
@@ -308,16 +320,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       // converged warp: waits by every lane, tcgen05 instructions by one elected lane (uniform operands)
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const int rc0 = (EPI == EPI_STATS && p.res_chunk0 > 0) ? p.res_chunk0 : total_chunks;  // dual: both TMEM halves
       for (int kc = 0; kc < total_chunks; kc += KSUB) {
-        const uint32_t d_tmem = tmem_base + ((kc >= rc0) ? BN : as * BN);
+        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE + ((kc >= rc0) ? BN : 0);
         const int kfirst = (kc >= rc0) ? rc0 : 0;
         mbar_wait(&full_bar[stage], phase);
-        if (tl && lane == 0 && kc == 0 && tile == (int)blockIdx.x) tl[3] = clock64();
+        if (tl && lane == 0 && kc == 0 && ti == 0) tl[3] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
         const uint64_t da = umma_desc_sw128(sa);
@@ -336,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (tl && lane == 0) tl[4] = clock64();
-      if (rc0 < total_chunks) { aphase ^= 1; }            // dual accumulator: one TMEM stage (as stays 0)
+      if (!DUAL_DOUBLE && rc0 < total_chunks) { aphase ^= 1; }   // dual accumulator with 256-wide tiles: one TMEM stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   } else if (warp >= 3) {
@@ -351,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t spar = smem_u32(s_par);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int n_tile = tile % p.n_tiles;
       const int r0 = (tile / p.n_tiles) * GEMM_BM;
       const int n0 = n_tile * BN;
@@ -361,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool row_ok = row < p.M;
 
       const uint32_t sp0 = spar + (n0 + cbase) * 4;  // bias of this warp's first column
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + cbase;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE + cbase;
 
       if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_LN || EPI == EPI_SNAKE) {
         const bool has_res = (EPI == EPI_LN) || (EPI == EPI_PLAIN && p.resid != nullptr);
@@ -376,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
-        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
+        if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
 
         float gs[(EPI == EPI_STATS) ? 2 * NCH : 1];
         float lsum = 0.f, lsq = 0.f;
@@ -387,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int c = 0; c < NCH; ++c) {
           float* v = vbuf[c & 1];
           tmem_ld_wait();
-          if (tl && ew == 0 && lane == 0 && c == 0 && tile == (int)blockIdx.x) tl[11] = clock64();
+          if (tl && ew == 0 && lane == 0 && c == 0 && ti == 0) tl[11] = clock64();
           if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -426,7 +438,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }
           epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
-          if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[12 + (c != 0)] = clock64();
+          if (tl && ew == 0 && lane == 0 && ti == 0) tl[12 + (c != 0)] = clock64();
         }
         if constexpr (EPI == EPI_STATS) {
           // deterministic per-(utterance, group) partial sums of this warp's 32 rows x 4 groups:
@@ -473,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __syncwarp();
           }
         }
-        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[14] = clock64();
+        if (tl && ew == 0 && lane == 0 && ti == 0) tl[14] = clock64();
         if constexpr (EPI == EPI_STATS) {
           if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
             __half* rob = p.res_out + (size_t)rw0 * p.ldo + n0 + cbase;
@@ -485,7 +497,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               if (c + 1 < NCH) tmem_ld32(taddr + BN + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b4 = lds_f4(spar + (512 + n0 + cbase + c * 32 + 4 * j) * 4);
+                const float4 b4 = lds_f4(spar + (256 + n0 + cbase + c * 32 + 4 * j) * 4);
                 v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
               }
               epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
@@ -532,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
-        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
+        if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
         if (n_tile < 2) {
           __half* dst = (n_tile == 0 ? p.q : p.k) + (size_t)rw0 * BN + cbase;
 #pragma unroll
@@ -566,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
-        if (tl && ew == 0 && lane == 0 && tile == (int)blockIdx.x) tl[5] = clock64();
+        if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int col0 = cbase + c * 32;
@@ -606,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (EPI == EPI_STATS && p.res_chunk0 > 0) { aphase ^= 1; }   // dual accumulator: single TMEM stage
+      if (!DUAL_DOUBLE && EPI == EPI_STATS && p.res_chunk0 > 0) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   }

@@ -486,7 +486,8 @@ template <int BN, int EPI, int KSUB>
 static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
                             const GemmParams& p, cudaStream_t stream, double aflops) {
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.n_tiles;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles = p.m_major ? m_tiles : m_tiles * p.n_tiles;   // m_major: one CTA per row tile, all its N tiles
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   GemmParams pp = p;
   pp.tl = nullptr;
@@ -561,7 +562,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
     p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
     p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
+    if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
   }
   const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
@@ -578,7 +579,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
+    if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
   }
   // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
@@ -680,7 +681,7 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     }
     // k3 convs: out rows * 256 * 768; ConvTranspose: B*H input rows * 512 outputs * 512 (two 2-tap phases)
     const double af = (mode == 2) ? 2.0 * w.B * (double)w.H * 512 * 512 : 2.0 * w.B * (double)lc.L * C * 3 * C;
-    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmap, p, stream, af); }
+    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; p.m_major = 1; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmap, p, stream, af); }
     return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream, af);
   };
 
@@ -708,7 +709,7 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(h->b_fin); p.out = H(w.y);
-    if (h->conv_bn == 128) { p.n_tiles = 2; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
+    if (h->conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;

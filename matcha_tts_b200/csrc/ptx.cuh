@@ -284,6 +284,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);   // round-to-nearest; values here are O(1..1e2), far from 65504
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// same, saturating at the fp16 range: used for the FF1/SnakeBeta intermediate, the only tensor whose magnitude is not
+// bounded by a normalisation layer (with trained weights an overflow would otherwise poison the row with inf/NaN)
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
   return __half22float2(h);
