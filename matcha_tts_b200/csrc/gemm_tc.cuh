@@ -105,6 +105,7 @@ struct GemmParams {
   long long* tl;
   int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
+  int dbg;         // debug experiments (tools/gemm_repeat.py): 1 skip global stores, 2 skip smem staging + stores, 4 skip TMEM loads
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -135,7 +136,8 @@ __device__ __forceinline__ uint32_t epi_st_addr(uint32_t st, int row, int unit) 
 }
 // store 32 fp32 values of "my" row as fp16, coalesced 64 B per row
 __device__ __forceinline__ void epi_store_h32(uint32_t st, int lane, const float* v, __half* gtile, int ld,
-                                              int rows_valid) {
+                                              int rows_valid, int dbg = 0) {
+  if (dbg & 2) return;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     sts128(epi_st_addr(st, lane, j), make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
@@ -145,7 +147,7 @@ __device__ __forceinline__ void epi_store_h32(uint32_t st, int lane, const float
   for (int it = 0; it < 4; ++it) {
     const int row = it * 8 + (lane >> 2), unit = lane & 3;
     const uint4 u = lds128(epi_st_addr(st, row, unit));
-    if (row < rows_valid) stg128(gtile + (size_t)row * ld + unit * 8, u);
+    if (row < rows_valid && !(dbg & 1)) stg128(gtile + (size_t)row * ld + unit * 8, u);
   }
   __syncwarp();
 }
@@ -394,13 +396,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         float lsum = 0.f, lsq = 0.f;
         __half* obase = p.out + (size_t)rw0 * p.ldo + n0 + cbase;
         float vbuf[2][32];  // accumulator chunk c+1 is fetched from TMEM while chunk c is processed
-        tmem_ld32(taddr, vbuf[0]);
+        if (!(p.dbg & 4)) tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           float* v = vbuf[c & 1];
           tmem_ld_wait();
           if (tl && ew == 0 && lane == 0 && c == 0 && ti == 0) tl[11] = clock64();
-          if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+          if (c + 1 < NCH && !(p.dbg & 4)) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = lds_f4(sp0 + (c * 32 + 4 * j) * 4);
@@ -437,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }
-          epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
+          epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid, p.dbg);
           if (tl && ew == 0 && lane == 0 && ti == 0) tl[12 + (c != 0)] = clock64();
         }
         if constexpr (EPI == EPI_STATS) {

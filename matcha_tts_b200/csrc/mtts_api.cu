@@ -18,6 +18,7 @@
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
 #include "gemm_tc.cuh"
+#include "ln_qkv.cuh"
 
 using namespace mtts;
 
@@ -186,11 +187,18 @@ struct MttsHandle {
   int conv_bn_h = 256;     // MTTS_BN_H: same at level T/2 (87 row tiles at B=64, T=344)
   bool a_prefetch = true;  // MTTS_NO_APREFETCH=1: no early L2 prefetch of the first activation tiles
   bool w_hint = true;      // MTTS_NO_WHINT=1: load weights without the L2 evict_last hint
+  bool fused_lnqkv = false; // MTTS_LNQKV=1: ln_qkv_kernel instead of the GroupNorm-apply+LayerNorm1 launch followed by the QKV GEMM (measured slower)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
   // every kernel of a chain is small (tens of tiles) and latency-bound on its own
   int nsub_override = 0;  // MTTS_NSUB in the environment; 0 = heuristic
+  // staggered chains (MTTS_STAGGER=1; off: measured slower, 7.03 vs 6.61 ms -- a chain's step time barely depends on
+  // its batch, so serialising the level-T blocks serialises the solve): the level-T parts of the chains' estimator
+  // evaluations take turns (cross-chain events), one chain at level T/2 while the other is at level T
+  bool stagger = false;
+  mutable bool pdl_break = false;  // next launch follows a cross-chain event wait: plain (non-programmatic) launch
+  std::vector<cudaEvent_t> ev_turn;
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> ev_join;
   cudaEvent_t ev_fork = nullptr;
@@ -471,7 +479,8 @@ static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 gr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (h->use_pdl && !h->profiling) ? 1 : 0;
+  cfg.numAttrs = (h->use_pdl && !h->profiling && !h->pdl_break) ? 1 : 0;
+  h->pdl_break = false;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -582,20 +591,36 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
   }
-  // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
-  {
-    GnParams g{};
-    g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
-    g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
-    g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
-  }
-  // q | k | v^T
-  {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, C, 0);
-    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
-    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
+  if (h->fused_lnqkv && h->fused_tail) {
+    // x_r = Mish(GN(y))*m + res ; a = LN1(x_r) (on chip) ; q | k | v^T = a Wqkv^T   -- one kernel
+    if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
+      LnQkvParams lp{};
+      lp.M = lc.rows; lp.L = lc.L; lp.Lp = lc.Lp; lp.S = w.S;
+      lp.y = H(w.y); lp.res = H(w.res); lp.stats_part = part;
+      lp.gamma = F(sw.gn2_g); lp.beta = F(sw.gn2_b); lp.ln_g = F(sw.ln1_g); lp.ln_b = F(sw.ln1_b);
+      lp.rowmask = lc.mask; lp.rowb = lc.rowb; lp.xr = H(w.xr);
+      lp.q = H(w.q); lp.k = H(w.k); lp.vt = H(w.vt); lp.Lpad = lc.Lpad; lp.w_hint = h->w_hint ? 1 : 0;
+      const int tiles = (lc.rows + 127) / 128;
+      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+      CUDA_TRY(launch_k(h, ln_qkv_kernel, dim3(grid), dim3(LQ_THREADS), LQ_SMEM, stream, sw.m_qkv.d3, lp));
+      launched(h);
+    }
+  } else {
+    // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
+    {
+      GnParams g{};
+      g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
+      g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
+      g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
+      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    }
+    // q | k | v^T
+    {
+      GemmParams p = base;
+      segs_taps(p, 1, kTap1, C, 0);
+      p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
+      if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
+    }
   }
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
@@ -649,8 +674,12 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
 // One estimator evaluation on the operand buffer X0 (z | mu | spks already staged, masked).
 // Writes zout = (zbase ? zbase + zscale * v : v) in (B, 80, T) fp32 and, if upd_x0, refreshes the
 // z channels of X0 with zout * mask for the next evaluation.
+// `parts` selects which section is enqueued (the staggered chain schedule interleaves them across chains):
+// EST_HEAD = stage 0 at level T, EST_HALF = everything at level T/2 (down conv .. up ConvTranspose),
+// EST_TAIL = stage 5, last level conv, final block, projection + ODE update.
+enum { EST_HEAD = 1, EST_HALF = 2, EST_TAIL = 4, EST_ALL = 7 };
 static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float* zout, const float* zbase, float zscale,
-                         bool upd_x0, cudaStream_t stream) {
+                         bool upd_x0, cudaStream_t stream, int parts = EST_ALL) {
   const WsLayout& w = P.w;
   char* ws = P.ws;
   const char* ar = h->arena;
@@ -686,20 +715,22 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
   };
 
   // down 0 @T
-  if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
-  // down 1 @T/2
-  if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
-  if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
-  // mid
-  if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
-  if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
-  // up 0 @T/2 : cat[x, skip1]
-  if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
-  {
+  if (parts & EST_HEAD)
+    if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
+  if (parts & EST_HALF) {
+    if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
+    // down 1 @T/2
+    if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
+    if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
+    // mid
+    if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
+    if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
+    // up 0 @T/2 : cat[x, skip1]
+    if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
     LevelCtx lc = lT;  // mask of the OUTPUT rows (level T), indexed 2*r + phase
     if (int e = level_conv(P.xU0s, h->m_up0, h->b_up0, lc, H(w.xU0), 2)) return e;
   }
+  if (!(parts & EST_TAIL)) return 0;
   // up 1 @T : cat[x, skip0]
   if (int e = run_stage(h, P, 5, lT, P.xU0, P.skip0, H(w.xU1s), t_off, t_stride, stream)) return e;
   if (int e = level_conv(P.xU1s, h->m_up1, h->b_up1, lT, H(w.xF), 0)) return e;
@@ -863,10 +894,12 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
+  if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
   if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("MTTS_BN_H")) h->conv_bn_h = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   build_tables(h);
   int ndev = 0;
@@ -888,6 +921,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(ln_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
   } else {
     cudaGetLastError();  // no GPU: tables/sizes still work (used by the CPU-side tests); compute calls will fail
@@ -901,6 +935,7 @@ void mtts_destroy(MttsHandle* h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   for (cudaStream_t st : h->side) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : h->ev_turn) cudaEventDestroy(ev);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
@@ -1014,12 +1049,85 @@ static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, cons
   return 0;
 }
 
+// One estimator evaluation of a solve: time-table row, destination, base and scale of the ODE update.
+struct EvalDesc { int t_idx; float* zout; const float* zbase; float zscale; };
+static void solve_evals(Plan& P, float* z, int n, int solver, std::vector<EvalDesc>* ev) {
+  const float dt = (float)(1.0 / (double)n);
+  float* zmid = reinterpret_cast<float*>(P.ws + P.w.zmid);
+  ev->clear();
+  for (int i = 0; i < n; ++i) {
+    if (solver == MTTS_SOLVER_EULER) ev->push_back(EvalDesc{i, z, z, dt});
+    else { ev->push_back(EvalDesc{2 * i, zmid, z, dt * 0.5f}); ev->push_back(EvalDesc{2 * i + 1, z, z, dt}); }
+  }
+}
+
+// Staggered schedule of the chains of one solve.  Per chain the work is  T_0 H_0 T_1 H_1 ... T_m  with
+// T_0 = prologue + head of evaluation 0, H_k = the level-T/2 part of evaluation k, T_k = tail of evaluation k-1 +
+// head of evaluation k.  The level-T blocks take turns across chains in the order (k, chain): chain c's T_k waits
+// for chain c-1's T_k, chain 0's T_k for the last chain's T_{k-1} -- while one chain holds the turn the others run
+// their level-T/2 blocks, whose kernels have half the row tiles, so the tiles of all running kernels fit the SMs.
+static int enqueue_solve_staggered(MttsHandle* h, const std::vector<Chunk>& chunks, std::vector<Plan*>& plans, float* z,
+                                   const float* mu, const float* mask, const float* spks, int n, int solver, int T,
+                                   cudaStream_t stream) {
+  const int nsub = (int)chunks.size();
+  const size_t NF = h->cfg.out_channels;
+  while ((int)h->ev_turn.size() < nsub) {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->ev_turn.push_back(ev);
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
+  for (int i = 1; i < nsub; ++i) CUDA_TRY(cudaStreamWaitEvent(h->side[i - 1], h->ev_fork, 0));
+  std::vector<std::vector<EvalDesc>> evals(nsub);
+  for (int c = 0; c < nsub; ++c) {
+    if (plans[c]->te_n != n || plans[c]->te_solver != solver) return fail(MTTS_ESTATE, "internal: time-embedding table not prepared");
+    solve_evals(*plans[c], z + (size_t)chunks[c].b0 * NF * T, n, solver, &evals[c]);
+  }
+  const int m = (int)evals[0].size();
+  for (int k = 0; k <= m; ++k) {
+    for (int c = 0; c < nsub; ++c) {
+      const Chunk& ck = chunks[c];
+      Plan& P = *plans[c];
+      cudaStream_t st = c == 0 ? stream : h->side[c - 1];
+      if (k == 0) {
+        if (int e = run_prologue(h, P, z + (size_t)ck.b0 * NF * T, mu + (size_t)ck.b0 * NF * T, mask + (size_t)ck.b0 * T,
+                                 spks ? spks + (size_t)ck.b0 * h->nspk : nullptr, st))
+          return e;
+      }
+      if (!(k == 0 && c == 0)) {
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_turn[c > 0 ? c - 1 : nsub - 1], 0));
+        h->pdl_break = true;
+      }
+      if (k > 0) {
+        const EvalDesc& d = evals[c][k - 1];
+        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_TAIL)) return e;
+      }
+      if (k < m) {
+        const EvalDesc& d = evals[c][k];
+        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_HEAD)) return e;
+      }
+      h->pdl_break = false;
+      CUDA_TRY(cudaEventRecord(h->ev_turn[c], st));
+      if (k < m) {
+        const EvalDesc& d = evals[c][k];
+        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_HALF)) return e;
+      }
+    }
+  }
+  for (int i = 1; i < nsub; ++i) {
+    CUDA_TRY(cudaEventRecord(h->ev_join[i - 1], h->side[i - 1]));
+    CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i - 1], 0));
+  }
+  return 0;
+}
+
 // all chains of one solve: chain 0 on `stream`, the others on forked side streams, joined at the end
 static int enqueue_solve_chains(MttsHandle* h, const std::vector<Chunk>& chunks, std::vector<Plan*>& plans, float* z,
                                 const float* mu, const float* mask, const float* spks, int n, int solver, int T,
                                 cudaStream_t stream) {
   const int nsub = (int)chunks.size();
   const size_t NF = h->cfg.out_channels;
+  if (nsub > 1 && h->stagger && h->launch_limit < 0) return enqueue_solve_staggered(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
   if (nsub > 1) {
     CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
     for (int i = 1; i < nsub; ++i) CUDA_TRY(cudaStreamWaitEvent(h->side[i - 1], h->ev_fork, 0));
@@ -1173,6 +1281,7 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
   CUtensorMap ma, mw;
   GemmParams p{};
   p.M = rows; p.bias = bias; p.out = static_cast<__half*>(out); p.ldo = N; p.mask_mul = 1;
+  if (const char* e = getenv("MTTS_DBG")) p.dbg = atoi(e);
   segs_taps(p, ntaps, shifts, C, 0);
   const int saved = h->launch_limit;
   h->launch_limit = -1;

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from matcha_tts_b200 import Decoder, _lib  # noqa: E402
 
-NAMES = ["conv1", "gnA", "conv2", "gnB", "qkv", "attn"] + \
+NAMES = ["conv1", "gnA", "conv2"] + (["lnqkv"] if os.environ.get("MTTS_LNQKV") == "1" and os.environ.get("MTTS_NO_TAIL") != "1" else ["gnB", "qkv"]) + ["attn"] + \
     (["to_out", "ff1", "ff2"] if os.environ.get("MTTS_NO_TAIL") == "1" else ["tail"])
 
 
