@@ -141,6 +141,8 @@ struct WsLayout {
   size_t maskT, maskH, rowbT, rowbH, npadT, npadH, tvals, te_e, te_h1, te_h2, te6, part;
   size_t x0, y, res, h1, xr, a, xa, q, k, o, vt, s;
   size_t skip0, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF, zmid;
+  size_t flags;   // two arrays of nflags ints: inter-CTA flags of the fused GroupNorm conv launches (ping-pong)
+  int nflags;
   size_t vt_bytes, total;
 };
 
@@ -153,6 +155,8 @@ struct Plan {
   WsLayout w;
   char* ws;
   int te_n = -1, te_solver = -1;  // the solver's time-embedding table in ws.te6 is valid for (n_timesteps, solver)
+  int flag_par = 0;     // which flag array the next fused GroupNorm launch uses
+  int grid_cap = 0;     // CTAs one flag-synchronised launch of this plan may use (#SMs / chains: all must be co-resident)
   LevelMaps lv[2];
   TMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
 };
@@ -188,6 +192,8 @@ struct MttsHandle {
   bool a_prefetch = true;  // MTTS_NO_APREFETCH=1: no early L2 prefetch of the first activation tiles
   bool w_hint = true;      // MTTS_NO_WHINT=1: load weights without the L2 evict_last hint
   bool fused_lnqkv = false; // MTTS_LNQKV=1: ln_qkv_kernel instead of the GroupNorm-apply+LayerNorm1 launch followed by the QKV GEMM (measured slower)
+  bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
+                           // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
@@ -197,6 +203,7 @@ struct MttsHandle {
   // its batch, so serialising the level-T blocks serialises the solve): the level-T parts of the chains' estimator
   // evaluations take turns (cross-chain events), one chain at level T/2 while the other is at level T
   bool stagger = false;
+  int gn_cap = 0;          // grid cap of the flag-synchronised launches being enqueued (set per plan)
   mutable bool pdl_break = false;  // next launch follows a cross-chain event wait: plain (non-programmatic) launch
   std::vector<cudaEvent_t> ev_turn;
   std::vector<cudaStream_t> side;
@@ -393,6 +400,8 @@ static bool ws_layout(const MttsHandle* h, int B, int T, WsLayout* w) {
   w->xM0 = alloc(2 * rH * C); w->xM1 = alloc(2 * rH * C); w->xU0s = alloc(2 * rH * C);
   w->xU0 = alloc(2 * rT * C); w->xU1s = alloc(2 * rT * C); w->xF = alloc(2 * rT * C);
   w->zmid = alloc(4ull * B * NF * T);
+  w->nflags = (int)align_up((rT + 127) / 128 + 1, 32);
+  w->flags = alloc(2ull * 4 * w->nflags);
   w->total = cur;
   return true;
 }
@@ -497,7 +506,8 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = p.m_major ? m_tiles : m_tiles * p.n_tiles;   // m_major: one CTA per row tile, all its N tiles
-  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  if (epi_is_gn(EPI) && h->gn_cap > 0 && grid > h->gn_cap) grid = h->gn_cap;
   GemmParams pp = p;
   pp.tl = nullptr;
   pp.w_hint = h->w_hint ? 1 : 0;
@@ -539,6 +549,33 @@ struct LevelCtx {
   const int* npad;
 };
 
+// The GroupNorm that follows a conv can be finished inside the conv launch (EPI_GNA / EPI_GNB) when a 128-row tile
+// touches at most GEMM_GN_MAXU utterances and the flag waits cannot form a cycle: every wait set (the row tiles of a
+// tile's utterances) is shorter than half the grid, or the launch has one tile per CTA.
+static bool gn_fusable(const MttsHandle* h, const Plan& P, const LevelCtx& lc) {
+  if (!h->fused_gn) return false;
+  const int maxu = 127 / lc.Lp + 2;
+  if (maxu > GEMM_GN_MAXU) return false;
+  const int tiles = (lc.rows + 127) / 128;
+  const int cap = P.grid_cap > 0 ? P.grid_cap : h->num_sms;
+  const int span = (maxu * lc.Lp + 127) / 128 + 1;
+  return tiles <= cap || 2 * span <= cap;
+}
+static void gn_fill(MttsHandle* h, Plan& P, const LevelCtx& lc, GemmParams& p, size_t gamma, size_t beta) {
+  const WsLayout& w = P.w;
+  int* fl = reinterpret_cast<int*>(P.ws + w.flags);
+  p.flags = fl + P.flag_par * w.nflags;
+  p.flags_clear = fl + (P.flag_par ^ 1) * w.nflags;
+  p.nflags = w.nflags;
+  P.flag_par ^= 1;
+  p.L = lc.L; p.nutt = w.B;
+  p.gn_g = reinterpret_cast<const float*>(h->arena + gamma);
+  p.gn_b = reinterpret_cast<const float*>(h->arena + beta);
+  p.rowmask = lc.mask; p.mask_mul = 1; p.mask_nstep = 0;
+  p.n_tiles = 1;
+  h->gn_cap = P.grid_cap > 0 ? P.grid_cap : h->num_sms;
+}
+
 // One resnet + transformer stage (reference ResnetBlock1D :785-790 + BasicTransformerBlock :733-744).
 static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TMap& in0, const TMap& in1,
                      __half* out, int t_off, int t_stride, cudaStream_t stream) {
@@ -554,6 +591,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
   const float* te6 = reinterpret_cast<const float*>(ws + w.te6);
 
   const int conv_bn = lc.lv ? h->conv_bn_h : h->conv_bn;
+  const bool fuse_gn = gn_fusable(h, P, lc);
   const double fr = 2.0 * w.B * (double)lc.L;   // algorithmic FLOPs = fr * N * K (valid rows, unpadded K/N)
   const int ci_real = (s == 0) ? h->cfg.in_channels : sw.src_cols[0] + sw.src_cols[1];
   GemmParams base{};
@@ -571,12 +609,17 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
     p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
     p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
+    if (fuse_gn) {   // ... and h1 = (Mish(GN(y))*m + temb)*m in the same launch
+      gn_fill(h, P, lc, p, sw.gn1_g, sw.gn1_b);
+      p.temb = te6 + (size_t)s * C; p.t_off = t_off; p.t_stride = t_stride; p.t_ld = 6 * C; p.out = H(w.h1);
+      if (int e = launch_gemm<256, EPI_GNA>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
+    }
+    else if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
   }
   const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
-  {
+  if (!fuse_gn) {
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
@@ -588,10 +631,21 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
+    if (fuse_gn) {   // ... and x_r = Mish(GN(y))*m + res ; a = LN1(x_r) in the same launch
+      gn_fill(h, P, lc, p, sw.gn2_g, sw.gn2_b);
+      p.resid = H(w.res); p.ln_g = F(sw.ln1_g); p.ln_b = F(sw.ln1_b); p.out = H(w.xr); p.out2 = H(w.a);
+      if (int e = launch_gemm<256, EPI_GNB>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
+    }
+    else if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
   }
-  if (h->fused_lnqkv && h->fused_tail) {
+  if (fuse_gn) {
+    // q | k | v^T
+    GemmParams p = base;
+    segs_taps(p, 1, kTap1, C, 0);
+    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
+    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
+  } else if (h->fused_lnqkv && h->fused_tail) {
     // x_r = Mish(GN(y))*m + res ; a = LN1(x_r) (on chip) ; q | k | v^T = a Wqkv^T   -- one kernel
     if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
       LnQkvParams lp{};
@@ -740,13 +794,19 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(h->b_fin); p.out = H(w.y);
-    if (h->conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
+    const bool fuse_gn = gn_fusable(h, P, lT);
+    if (fuse_gn) {
+      gn_fill(h, P, lT, p, h->gnf_g, h->gnf_b);
+      p.temb = nullptr; p.out = H(w.h1);
+      if (int e = launch_gemm<256, EPI_GNA>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e;
+    }
+    else if (h->conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
     const dim3 gn_grid((lT.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -799,6 +859,8 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
   char* ws = P.ws;
   auto Fw = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   // V^T pad columns [L, Lpad) are zeroed once with the whole workspace (get_plan) and never written afterwards
+  CUDA_TRY(cudaMemsetAsync(ws + w.flags, 0, 2ull * 4 * w.nflags, stream));   // inter-CTA flags of the fused GroupNorm launches
+  P.flag_par = 0;
   if (can_launch(h)) {
     mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
                                               reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
@@ -901,6 +963,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
@@ -916,6 +979,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     int e = 0;
+    e |= set_gemm_attr<256, EPI_GNA>(); e |= set_gemm_attr<256, EPI_GNB>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
     e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
     e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
@@ -1023,6 +1087,7 @@ int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Plan* P;
   if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
+  P->grid_cap = h->num_sms;
   h->launch_count = 0;
   CUDA_TRY(cudaMemcpyAsync(P->ws + P->w.tvals, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream));
   P->te_n = -1;  // per-utterance times: not a solver table
@@ -1166,6 +1231,7 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
   for (int i = 0; i < nsub; ++i) {
     const size_t avail = (i + 1 < nsub ? chunks[i + 1].ws_off : need) - chunks[i].ws_off;
     if (int e = get_plan(h, static_cast<char*>(workspace) + chunks[i].ws_off, avail, chunks[i].nb, T, stream, &plans[i])) return e;
+    plans[i]->grid_cap = h->num_sms / nsub;   // concurrent chains: their flag-synchronised launches must all fit the SMs
   }
   h->launch_count = 0;
   for (int i = 0; i < nsub; ++i) {   // time-embedding tables: once per (plan, n_timesteps, solver), outside the graph
