@@ -8,23 +8,24 @@
 //
 // One CTA per SM, persistent over row tiles.  Neither c (128x256) nor s (128x1024) ever leaves the SM:
 //   TMEM  cols [0,256)   R : to_out accumulator -> x_a (fp32, written back by the epilogue) -> FF2 accumulates on top
-//         cols [256,384) D1[2] : double-buffered FF1 accumulator, one 64-wide chunk of the hidden dimension each
+//         cols [256,384) D1 : FF1 accumulator, one 128-wide chunk of the hidden dimension (single buffer: the epilogue
+//                             moves it to registers at once, then FF1 of the next chunk may overwrite it)
 //         cols [384,512) Cc : c = LayerNorm3(x_a) as packed fp16 pairs -- the A operand of FF1 is read from TENSOR
-//                             MEMORY (an N=64 MMA reading a 4 KB A tile from shared memory every 32 cycles would be
-//                             shared-memory-bandwidth bound)
-//   SMEM  S  3x16 KB : s chunk j (128x64 fp16), three buffers (A operand of FF2)
+//                             MEMORY.  The tensor-memory A read costs ~64 cycles per K16 step whatever N is (measured:
+//                             16 N=64 steps took 0.5 us, not 0.26), so FF1 uses N=128 steps (64 cycles each anyway)
+//   SMEM  S  2x32 KB : s chunk j (128x128 fp16 as two 128B-swizzled 128x64 K tiles), two buffers (A operand of FF2)
 //         ring 4x32 KB : TMA-fed operand pieces, ONE cp.async.bulk.tensor each -- an issue costs the thread
 //                        ~330 cycles whatever the box size (profiles/r01_tma_issue_microbench.txt), so pieces
 //                        are as large as a 512-cycle MMA group needs:
 //                          o  tile    box {64, 128 rows, 2 K-chunks} of o  viewed as [2][rows][64]
 //                          Wo K-chunk box {64, 256 rows}                 (B operand, N = 256)
-//                          W1 chunk j box {64, 64 rows, 4 K-chunks}  of W1 viewed as [4][1024][64] (N = 64, K = 256)
-//                          W2 chunk j box {64, 256 rows}                 (B operand, N = 256, K = 64)
+//                          W1 chunk j, half h: box {64, 128 rows, 2 K-chunks} of W1 viewed as [4][1024][64] (N = 128, K = 128)
+//                          W2 chunk j, half h: box {64, 256 rows}        (B operand, N = 256, K = 64)
 // Warp roles: warp 0 TMA producer, warp 1 issues to_out + FF1, warp 2 issues FF2 (two issuers: the tcgen05 queue is
 // short, so every barrier wait / commit of a single issuer idles the tensor pipe), warps 3-18 epilogue (four column
-// groups per TMEM lane quarter).  The MMA stream is software-pipelined over the 16 hidden chunks
-//   FF1_0 FF1_1 | FF2_0 FF1_2 | FF2_1 FF1_3 | ... | FF2_14 | FF2_15
-// so that the tensor pipe works on FF2_{j-1} and FF1_{j+1} while the epilogue warps apply SnakeBeta to chunk j.
+// groups per TMEM lane quarter).  The MMA stream is software-pipelined over the 8 hidden chunks
+//   FF1_0 | FF1_1 FF2_0 | FF1_2 FF2_1 | ... | FF1_7 FF2_6 | FF2_7
+// so that the tensor pipe works on FF1_{j+1} and FF2_{j-1} while the epilogue warps apply SnakeBeta to chunk j.
 #pragma once
 #include <cuda.h>
 
@@ -51,20 +52,22 @@ struct TailParams {
 
 constexpr int TAIL_NST = 4;
 constexpr int TAIL_PIECE = 32768;
-constexpr int TAIL_NSB = 3;                                           // s chunk buffers (FF1 runs two chunks ahead of FF2)
-constexpr int TAIL_NJ = 16;                                           // hidden chunks of 64
+constexpr int TAIL_NSB = 2;                                           // s chunk buffers
+constexpr int TAIL_SBYTES = 32768;                                    // one s chunk: 128 rows x 128 fp16
+constexpr int TAIL_NJ = 8;                                            // hidden chunks of 128
 constexpr int TAIL_NCG = 4;                                           // column groups -> 16 epilogue warps (4 per scheduler)
 constexpr int TAIL_THREADS = 96 + 128 * TAIL_NCG;                      // producer, two MMA issuers, 16 epilogue warps
-constexpr int TAIL_OFF_S = 0;                                         // 3 x 16 KB
-constexpr int TAIL_OFF_RING = TAIL_OFF_S + TAIL_NSB * 16384;          // 49152
-constexpr int TAIL_OFF_PAR = TAIL_OFF_RING + TAIL_NST * TAIL_PIECE;   // 180224
+constexpr int TAIL_OFF_S = 0;                                         // 2 x 32 KB
+constexpr int TAIL_OFF_RING = TAIL_OFF_S + TAIL_NSB * TAIL_SBYTES;    // 65536
+constexpr int TAIL_OFF_PAR = TAIL_OFF_RING + TAIL_NST * TAIL_PIECE;   // 196608
 constexpr int TAIL_PAR_FLOATS = 4 * 256 + 3 * 1024;                   // b_o ln_g ln_b b2 | b1 sn_a sn_ib
 // epilogue staging (16 warps x 32 rows x 64 B = 32 KB) aliases the S buffers: it is only used at the start (E1)
 // and at the end (E3) of a tile, when no FF2 MMA can be reading S (r_full / r_done imply all MMAs retired)
 constexpr int TAIL_OFF_STAGING = TAIL_OFF_S;
-constexpr int TAIL_OFF_RED = TAIL_OFF_PAR + TAIL_PAR_FLOATS * 4;      // 212992: LayerNorm partials [128][NCG] float2
-constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;       // 217088
-constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;                         // 217344
+constexpr int TAIL_OFF_RED = TAIL_OFF_PAR + TAIL_PAR_FLOATS * 4;      // LayerNorm partials [128][NCG] float2
+constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;
+constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;
+static_assert(TAIL_SMEM <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmWo,
@@ -73,8 +76,8 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   constexpr int NEW = 4 * NCG;       // epilogue warps
   constexpr int CW1 = 256 / NCG;     // columns per warp in the 256-wide phases
   constexpr int NCH1 = CW1 / 32;
-  constexpr int CW2 = 64 / NCG;      // columns per warp in a 64-wide FF1 chunk (= 16: one TMEM load)
-  static_assert(CW2 == 16, "one 16-column TMEM load per thread and hidden chunk");
+  constexpr int CW2 = 128 / NCG;     // columns per warp in a 128-wide FF1 chunk (= 32: one TMEM load)
+  static_assert(CW2 == 32, "one 32-column TMEM load per thread and hidden chunk");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -84,10 +87,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   uint64_t* empty_bar = bars + TAIL_NST;            // [TAIL_NST]
   uint64_t* r_full = bars + 2 * TAIL_NST;           // to_out accumulator complete
   uint64_t* c_ready = r_full + 1;                   // c written to TMEM, x_a written back to TMEM
-  uint64_t* d1_full = r_full + 2;                   // [2] FF1 chunk accumulator complete
-  uint64_t* d1_empty = r_full + 4;                  // [2] epilogue has read the FF1 chunk accumulator
-  uint64_t* s_ready = r_full + 6;                   // [3] s chunk written to smem
-  uint64_t* s_empty = r_full + 9;                   // [3] FF2 has consumed the s chunk
+  uint64_t* d1_full = r_full + 2;                   // FF1 chunk accumulator complete ([1] unused)
+  uint64_t* d1_empty = r_full + 4;                  // epilogue has read the FF1 chunk accumulator ([1] unused)
+  uint64_t* s_ready = r_full + 6;                   // [2] s chunk written to smem
+  uint64_t* s_empty = r_full + 9;                   // [2] FF2 has consumed the s chunk
   uint64_t* r_done = r_full + 12;                   // all FF2 MMAs of the tile complete
   uint64_t* r_empty = r_full + 13;                  // epilogue has read the final accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 14);
@@ -144,14 +147,16 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         }
         __syncwarp();
       };
-      auto put_w1 = [&](int j) {
-        const uint32_t slot = slot_acquire();
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
-          if (p.w_hint) tma_load_3d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 64, 0, pol);
-          else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 64, 0);
+      auto put_w1 = [&](int j) {   // hidden units [128j, 128j+128): two pieces of K = 128 each
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t slot = slot_acquire();
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
+            if (p.w_hint) tma_load_3d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh, pol);
+            else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       };
       bool first = true;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
@@ -168,9 +173,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         }
         put_w1(0);
         put_w1(1);
-        for (int j = 0; j < TAIL_NJ; ++j) {
+        for (int j = 0; j < TAIL_NJ; ++j) {   // tensor-pipe order: FF1_{j+1} FF2_j FF1_{j+2} FF2_{j+1} ...
+          put2(&tmW2, j * 128, 0);
+          put2(&tmW2, j * 128 + 64, 0);
           if (j + 2 < TAIL_NJ) put_w1(j + 2);
-          put2(&tmW2, j * 64, 0);
         }
       }
     }
@@ -180,7 +186,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     // issued by one elected lane.  Warp 1 owns the to_out + FF1 stream (accumulators R then D1), warp 2 the FF2
     // stream (accumulates into R); both walk the same ring-item numbering as the producer.
     constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
-    constexpr uint32_t idesc64 = umma_idesc_f16(128, 64);
+    constexpr uint32_t idesc128 = umma_idesc_f16(128, 128);
     const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
     const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
     auto slot_wait = [&](uint32_t item) -> uint32_t {
@@ -189,14 +195,15 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       tc_fence_after();
       return ring + slot * TAIL_PIECE;
     };
-    // ring items of one tile: 0,1 Wo K-chunks | 2 o | W1_0, W1_1 | then (W1_{j+2}, W2_j) for j = 0..15
-    auto item_w1 = [](int k) -> uint32_t { return k < 2 ? 3u + k : 2u * k + 1u; };
-    auto item_w2 = [](int j) -> uint32_t { return j <= 13 ? 6u + 2u * j : 19u + j; };
+    // ring items of one tile (two per chunk operand): 0,1 Wo K-chunks | 2 o | W1_0 (3,4) W1_1 (5,6) | then for j = 0..7:
+    // W2_j (2 items), W1_{j+2} (2 items, while it exists)
+    auto item_w1 = [](int k) -> uint32_t { return k < 2 ? 3u + 2u * k : 4u * k + 1u; };          // first of two
+    auto item_w2 = [](int j) -> uint32_t { return j <= 5 ? 7u + 4u * j : 31u + 2u * (j - 6); };  // first of two
     constexpr uint32_t ITEMS = 35;
     long long* tl = (p.tl != nullptr) ? p.tl + (size_t)blockIdx.x * 128 : nullptr;
     uint32_t n_tile = 0;
     if (warp == 1) {
-      uint32_t n_d1e0 = 0, n_d1e1 = 0;
+      uint32_t n_d1e = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
         if (n_tile != 0) tl = nullptr;
         const uint32_t base = n_tile * ITEMS;
@@ -224,25 +231,25 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tc_fence_after();
         if (tl && lane == 0) tl[2] = clock64();
         for (int j = 0; j < TAIL_NJ; ++j) {
-          const int b = j & 1;
-          uint32_t& n = b ? n_d1e1 : n_d1e0;
-          mbar_wait(&d1_empty[b], (n & 1) ^ 1);
-          ++n;
+          mbar_wait(&d1_empty[0], (n_d1e & 1) ^ 1);
+          ++n_d1e;
           tc_fence_after();
           if (tl && lane == 0 && j < 8) tl[4 + 4 * j] = clock64();
-          const uint32_t item = base + item_w1(j);
-          const uint32_t w = slot_wait(item);
-          const uint64_t db0 = umma_desc_sw128(w);
-          if (elect_one()) {
+          for (int hh = 0; hh < 2; ++hh) {   // K halves: one ring piece [2 K-chunks][128 hidden units][64]
+            const uint32_t item = base + item_w1(j) + hh;
+            const uint32_t w = slot_wait(item);
+            const uint64_t db0 = umma_desc_sw128(w);
+            if (elect_one()) {
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc)
+              for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B descriptor address in 16-byte units
-                umma_f16_ts(tD1 + b * 64, tC + kc * 32 + kk * 8, db0 + kc * (8192 >> 4) + 2 * kk, idesc64, (kc | kk) != 0);
-            umma_commit(&empty_bar[item % TAIL_NST]);
-            umma_commit(&d1_full[b]);
+                for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B descriptor address in 16-byte units
+                  umma_f16_ts(tD1, tC + (2 * hh + sub) * 32 + kk * 8, db0 + sub * (16384 >> 4) + 2 * kk, idesc128, (hh | sub | kk) != 0);
+              umma_commit(&empty_bar[item % TAIL_NST]);
+              if (hh == 1) umma_commit(&d1_full[0]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (tl && lane == 0 && j < 8) tl[5 + 4 * j] = clock64();
         }
       }
@@ -259,17 +266,21 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           ++n_sr;
           tc_fence_after();
           if (tl && lane == 0 && j < 8) tl[6 + 4 * j] = clock64();
-          const uint32_t item = base + item_w2(j);
-          const uint32_t w = slot_wait(item);
-          const uint64_t da = umma_desc_sw128(sbuf + b * 16384), db = umma_desc_sw128(w);
-          if (elect_one()) {
+          for (int hh = 0; hh < 2; ++hh) {   // K halves: s K tile hh x W2 piece hh
+            const uint32_t item = base + item_w2(j) + hh;
+            const uint32_t w = slot_wait(item);
+            const uint64_t da = umma_desc_sw128(sbuf + b * TAIL_SBYTES + hh * 16384), db = umma_desc_sw128(w);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
-            umma_commit(&empty_bar[item % TAIL_NST]);
-            umma_commit(&s_empty[b]);
-            if (j == TAIL_NJ - 1) umma_commit(r_done);
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
+              umma_commit(&empty_bar[item % TAIL_NST]);
+              if (hh == 1) {
+                umma_commit(&s_empty[b]);
+                if (j == TAIL_NJ - 1) umma_commit(r_done);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (tl && lane == 0 && j < 8) tl[7 + 4 * j] = clock64();
         }
       }
@@ -359,29 +370,28 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         if (lane == 0) mbar_arrive(c_ready);
         if (tl) tl[1] = clock64();
       }
-      // ------------------------------------------------ E2: SnakeBeta on the 16 hidden chunks
+      // ------------------------------------------------ E2: SnakeBeta on the 8 hidden chunks
 #pragma unroll 1
       for (int j = 0; j < TAIL_NJ; ++j) {
-        const int b = j & 1;                 // accumulator buffer
         const uint32_t sb = n_s % TAIL_NSB;  // s buffer
         if (lane == 0) {
-          mbar_wait(&s_empty[sb], ((n_s / TAIL_NSB) & 1) ^ 1);  // FF2_{j-3} no longer reads S[sb]
-          mbar_wait(&d1_full[b], n_d1f[b] & 1);
+          mbar_wait(&s_empty[sb], ((n_s / TAIL_NSB) & 1) ^ 1);  // FF2_{j-2} no longer reads S[sb]
+          mbar_wait(&d1_full[0], n_d1f[0] & 1);
         }
         ++n_s;
-        ++n_d1f[b];
+        ++n_d1f[0];
         __syncwarp();
         tc_fence_after();
         if (tl && j < 8) tl[4 + 2 * j] = clock64();
-        float v[16];
-        tmem_ld16(tD1 + b * 64 + lane_off + cg * 16, v);
+        float v[32];
+        tmem_ld32(tD1 + lane_off + cg * 32, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&d1_empty[b]);  // the accumulator chunk is in registers: FF1_{j+2} may overwrite it
-        const uint32_t pb = spar + (1024 + j * 64 + cg * 16) * 4;
+        if (lane == 0) mbar_arrive(&d1_empty[0]);  // the accumulator chunk is in registers: FF1_{j+1} may overwrite it
+        const uint32_t pb = spar + (1024 + j * 128 + cg * 32) * 4;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 8; ++jj) {
           const float4 b4 = lds_f4(pb + jj * 16);
           const float4 a4 = lds_f4(pb + 4096 + jj * 16);
           const float4 i4 = lds_f4(pb + 8192 + jj * 16);
@@ -391,10 +401,11 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           x = v[4 * jj + 2] + b4.z; sn = fast_sin(x * a4.z); v[4 * jj + 2] = fmaf(sn * sn, i4.z, x);
           x = v[4 * jj + 3] + b4.w; sn = fast_sin(x * a4.w); v[4 * jj + 3] = fmaf(sn * sn, i4.w, x);
         }
-        const uint32_t srow = sbuf + sb * 16384 + trow * 128;
+        // chunk columns cg*32 .. +32 -> K tile cg/2, 16-byte units (cg%2)*4 .. +4 of the row (128B swizzle)
+        const uint32_t srow = sbuf + sb * TAIL_SBYTES + (cg >> 1) * 16384 + trow * 128;
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-          sts128(srow + (((cg * 2 + u) ^ (trow & 7)) << 4),
+        for (int u = 0; u < 4; ++u)
+          sts128(srow + ((((cg & 1) * 4 + u) ^ (trow & 7)) << 4),
                  make_uint4(pack_h2_sat(v[8 * u], v[8 * u + 1]), pack_h2_sat(v[8 * u + 2], v[8 * u + 3]),
                             pack_h2_sat(v[8 * u + 4], v[8 * u + 5]), pack_h2_sat(v[8 * u + 6], v[8 * u + 7])));
         fence_proxy_async_smem();

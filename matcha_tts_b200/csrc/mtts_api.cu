@@ -133,7 +133,7 @@ struct StageW {
   size_t c1_b, gn1_g, gn1_b, c2_b, gn2_g, gn2_b, res_b, ln1_g, ln1_b, o_b, ln3_g, ln3_b, ff1_b, sn_a, sn_ib, ff2_b;
   TMap m_c1, m_c2, m_qkv;
   CUtensorMap m_wo, m_ff1, m_ff2;
-  CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 64, 4}: one hidden chunk of the fused tail (ff_tail.cuh)
+  CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 128, 2}: half (K = 128) of one 128-wide hidden chunk of the fused tail (ff_tail.cuh)
 };
 
 struct WsLayout {
@@ -354,7 +354,7 @@ static int build_weight_maps(MttsHandle* h) {
     if (make_map(&w.m_wo, a + w.wo, C, 128, 128, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff2, a + w.ff2, C, 4 * C, 4 * C, 256)) return MTTS_ECUDA;
-    if (make_map3(&w.t_ff1, a + w.ff1, 4 * C, 4, C, 64)) return MTTS_ECUDA;
+    if (make_map3(&w.t_ff1, a + w.ff1, 4 * C, 4, C, 128, 2)) return MTTS_ECUDA;
   }
   if (make_tmap(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
   if (make_tmap(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
