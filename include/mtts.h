@@ -93,6 +93,12 @@ int mtts_euler_solve(MttsHandle* h, float* z_inout, const float* mu, const float
                      int n_timesteps, int solver, void* workspace, size_t workspace_bytes, int B, int T,
                      int use_graph, void* stream);
 
+/* Utterance chains per solve: a solve of B utterances is split into n independent sub-batches on forked streams (graph
+ * branches) whose latency-bound kernels overlap.  0 = heuristic (two chains for large batches -- best when ONE solve is
+ * in flight); a host that keeps several solves in flight on several handles/streams sets 1 (the solves overlap each
+ * other instead).  Takes effect for the following mtts_euler_solve / mtts_workspace_bytes calls. */
+int mtts_set_chains(MttsHandle* h, int n);
+
 /* Number of kernels enqueued by the last estimator_forward / euler_solve call on this handle. */
 int mtts_last_launch_count(const MttsHandle* h);
 

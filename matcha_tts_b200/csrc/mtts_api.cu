@@ -1274,6 +1274,17 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
   return 0;
 }
 
+int mtts_set_chains(MttsHandle* h, int n) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  if (n < 0 || n > 8) return fail(MTTS_EINVAL, "chains must be in [0, 8]");
+  if (n != h->nsub_override) {   // the captured graphs embed the chain structure
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    h->graphs.clear();
+  }
+  h->nsub_override = n;
+  return 0;
+}
+
 int mtts_last_launch_count(const MttsHandle* h) { return h ? h->launch_count : 0; }
 
 int mtts_debug_profile_begin(MttsHandle* h, void* stream) {

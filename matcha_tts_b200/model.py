@@ -229,12 +229,20 @@ class _Engine:
     def launch_count(self) -> int:
         return self.lib.mtts_last_launch_count(self.h)
 
+    def set_chains(self, n: int):
+        """Utterance chains per solve (0 = heuristic; 1 when several solves are kept in flight on several streams)."""
+        _lib.check(self.lib.mtts_set_chains(self.h, int(n)))
+        self.ws.clear()            # the workspace size depends on the chain layout
+
 
 # ----------------------------------------------------------------------------------------------
 # Decoder: the U-Net estimator
 # ----------------------------------------------------------------------------------------------
 class Decoder(nn.Module):
     """1-D U-Net vector-field estimator; constructor/forward as reference model.py:834-1048."""
+
+    MAX_ENGINES = 8
+    chains = 0      # utterance chains per solve for engines created from now on (see set_chains)
 
     def __init__(self, in_channels, out_channels, channels=(256, 256), dropout=0.05, attention_head_dim=64,
                  n_blocks=1, num_mid_blocks=2, num_heads=4, time_emb_dim=None, time_mlp_dim=None, ffn_mult=4,
@@ -261,7 +269,9 @@ class Decoder(nn.Module):
                     node.add_module(part, _Node())
                 node = node._modules[part]
             node.register_parameter(leaf, nn.Parameter(_init_param(key, shape, shapes), requires_grad=False))
-        self._engines: Dict[torch.device, _Engine] = {}
+        # one native engine (libmtts handle + packed weights + workspace + CUDA graphs) per (device, CUDA stream):
+        # solves issued on different streams are independent "lanes" that overlap on the GPU
+        self._engines: Dict[Tuple[torch.device, int], _Engine] = {}
 
     # -- native plumbing ---------------------------------------------------------------------
     def _cfg(self) -> _lib.MttsConfig:
@@ -276,10 +286,15 @@ class Decoder(nn.Module):
             raise RuntimeError("matcha_tts_b200.Decoder runs on CUDA (sm_100a) only; there is no CPU path")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        eng = self._engines.get(device)
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        eng = self._engines.get(key)
         if eng is None:
+            if len(self._engines) >= self.MAX_ENGINES:      # bound the handles a stream-hopping caller can create
+                self._engines.pop(next(iter(self._engines)))
             eng = _Engine(self._cfg(), device)
-            self._engines[device] = eng
+            if self.chains:
+                eng.set_chains(self.chains)
+            self._engines[key] = eng
         ver = self._weights_version()
         if eng.packed_version != ver:
             sd = {k: v for k, v in self.state_dict().items()}
@@ -333,9 +348,16 @@ class Decoder(nn.Module):
         eng.solve(z32, self._f32c(mu), self._f32c(mask), self._f32c(spks), int(n_timesteps), codes[solver], use_graph)
         return z32.to(z.dtype)
 
+    def set_chains(self, n: int):
+        """Utterance chains per solve: 0 = heuristic (best for one solve at a time), 1 = no split (use it when several
+        solves are in flight on several CUDA streams: each stream has its own engine and they overlap each other)."""
+        self.chains = int(n)
+        for eng in self._engines.values():
+            eng.set_chains(self.chains)
+
     def last_launch_count(self, device=None) -> int:
-        eng = next(iter(self._engines.values())) if device is None else self._engines[device]
-        return eng.launch_count()
+        engs = [e for (d, _), e in self._engines.items() if device is None or d == torch.device(device)]
+        return engs[-1].launch_count()
 
 
 # ----------------------------------------------------------------------------------------------

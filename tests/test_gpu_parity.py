@@ -297,3 +297,67 @@ def test_bucketed_multispeaker_matches_oracle(vctk):
             ma, rl = O.parity_errors(out[i][None], ref[row:row + 1, :, :n], mask[row:row + 1, :, :n])
             assert out[i].shape == (80, n)
             assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (i, ma, rl)
+
+
+# ---------------------------------------------------------------------------------------------
+# solve lanes: one native engine per CUDA stream, several solves in flight
+# ---------------------------------------------------------------------------------------------
+def test_concurrent_lanes_match_serial(lj):
+    dec, cfg, sd = lj
+    B, T, n = 8, 344, 10
+    ins = [O.make_inputs(cfg, B, T, None, seed=60 + i) for i in range(3)]
+    serial = [dec.solve(_d(z0), _d(mu), _d(mask), n, None, "euler", use_graph=True) for mu, mask, z0, _ in ins]
+    lanes = [torch.cuda.Stream() for _ in ins]
+    torch.cuda.synchronize()
+    outs = [None] * len(ins)
+    for rep in range(2):                      # second round replays the lanes' cached graphs
+        for i, (ls, (mu, mask, z0, _)) in enumerate(zip(lanes, ins)):
+            ls.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(ls):
+                outs[i] = dec.solve(_d(z0), _d(mu), _d(mask), n, None, "euler", use_graph=True)
+        torch.cuda.synchronize()
+        for a, b in zip(serial, outs):
+            assert torch.equal(a, b)          # a lane changes nothing but the stream
+    assert len({id(e) for e in dec._engines.values()}) >= 4   # default stream + three lanes
+
+
+def test_chains_setting_keeps_results(lj):
+    dec, cfg, sd = lj
+    B, T, n = 52, 344, 4                      # 52 x 346 rows >= 16384: the heuristic splits into two chains
+    mu, mask, z0, _ = O.make_inputs(cfg, B, T, None, seed=70)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        za = dec.solve(_d(z0), _d(mu), _d(mask), n, None, "euler", use_graph=True)
+        dec.set_chains(1)
+        zb = dec.solve(_d(z0), _d(mu), _d(mask), n, None, "euler", use_graph=True)
+        dec.set_chains(0)
+        zc = dec.solve(_d(z0), _d(mu), _d(mask), n, None, "euler", use_graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(za, zc)
+    ma, rl = O.parity_errors(zb.cpu(), za.cpu(), mask)     # chain boundaries regroup the GroupNorm partial sums
+    assert ma <= 5e-3 and rl <= 5e-4, (ma, rl)
+
+
+# ---------------------------------------------------------------------------------------------
+# opt-in kernel variants (environment switches read at handle creation) stay parity-green
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env", ["MTTS_GNFUSE", "MTTS_LNQKV", "MTTS_STAGGER", "MTTS_NO_TAIL", "MTTS_NO_PDL"])
+def test_opt_in_variants(env):
+    old = os.environ.get(env)
+    os.environ[env] = "1"
+    if env == "MTTS_STAGGER":
+        os.environ["MTTS_NSUB"] = "2"
+    try:
+        dec, cfg, sd = U.make_decoder(160)
+        mu, mask, z0, _ = O.make_inputs(cfg, 3, 344, [344, 301, 222], seed=80)
+        zr = O.euler_solve(sd, cfg, z0, mu, mask, 4)
+        for use_graph in (False, True):
+            z = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "euler", use_graph=use_graph).cpu()
+            ma, rl = O.parity_errors(z, zr, mask)
+            assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (env, use_graph, ma, rl)
+    finally:
+        os.environ.pop("MTTS_NSUB", None)
+        if old is None:
+            os.environ.pop(env, None)
+        else:
+            os.environ[env] = old
