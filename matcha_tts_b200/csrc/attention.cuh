@@ -29,6 +29,7 @@ struct AttnParams {
   const int* npad;       // [B] number of frames with mask == 0
   const __half* vt;      // [(b*2+h)*64 + d][Lpad]
   __half* out;           // [rows][128]
+  int pdl_late;          // 1: release the dependent launch after the key/value loop instead of at entry
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -47,7 +48,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bar_o = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int rowbase = b * p.Lp;
@@ -84,6 +85,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) s_mean[d] = acc / (float)npad;
     }
     __syncthreads();
+    if (p.pdl_late) pdl_launch_dependents();
     if (my_t < p.L) {
       uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64);
 #pragma unroll
@@ -222,6 +224,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncwarp();
   }
 
+  if (p.pdl_late) pdl_launch_dependents();
   if (my_t < p.L) {
     const float inv = 1.f / l_run;
     uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64);

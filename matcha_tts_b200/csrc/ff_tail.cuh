@@ -47,6 +47,7 @@ struct TailParams {
   const float* rowmask;  // [rows]
   __half* out;           // [rows, 256]
   int w_hint;            // 1: weight pieces are loaded with the L2 evict_last policy
+  int pdl_late;          // 1: griddepcontrol.launch_dependents at the last tile's final epilogue instead of at entry
   long long* tl;         // debug timeline [gridDim.x][128] clock64 stamps of the first tile (null in production)
 };
 
@@ -97,7 +98,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   static_assert((2 * TAIL_NST + 15) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();   // late: when the CTA's last tile reaches its final epilogue (see gemm_tc.cuh)
   const int m_tiles = (p.M + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -417,7 +418,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       {
         float mrow = 0.f;
         if (row < p.M) mrow = p.rowmask[row];
-        if (lane == 0) mbar_wait(r_done, n_tile & 1);
+        if (lane == 0) {
+          mbar_wait(r_done, n_tile & 1);
+          if (p.pdl_late && tile + (int)gridDim.x >= m_tiles) pdl_launch_dependents();
+        }
         __syncwarp();
         tc_fence_after();
         if (tl) tl[2] = clock64();

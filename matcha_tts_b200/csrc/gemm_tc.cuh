@@ -123,6 +123,7 @@ struct GemmParams {
   int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
   int dbg;         // debug experiments (tools/gemm_repeat.py): 1 skip global stores, 2 skip smem staging + stores, 4 skip TMEM loads
+  int pdl_late;    // 1: griddepcontrol.launch_dependents when the CTA's last accumulator is complete instead of at entry
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -231,7 +232,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_launch_dependents();  // the next kernel may start its prologue; it still waits for our completion
+  // The next kernel may start its prologue (it still waits for our completion).  Early: at once -- best when one solve
+  // is in flight.  Late (p.pdl_late): when this CTA's last accumulator is complete -- with several solves in flight the
+  // dependents' CTAs would otherwise sit on SM slots (shared memory, TMEM) that another solve's ready kernels could use.
+  if (!p.pdl_late) pdl_launch_dependents();
   long long* tl = p.tl ? p.tl + (size_t)blockIdx.x * 16 : nullptr;
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); tl[8] = (long long)globaltimer_ns(); }
 
@@ -402,6 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int row = rw0 + lane;        // my row
       const int rows_valid = min(32, p.M - rw0);  // may be <= 0
       const bool row_ok = row < p.M;
+      const bool last_tile = p.pdl_late && cta_tile(ti + 1) < 0;
 
       const uint32_t sp0 = spar + (n0 + cbase) * 4;  // bias of this warp's first column
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE + cbase;
@@ -416,7 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int myb = -1;
         if constexpr (EPI == EPI_STATS) if (row_ok) myb = p.rowb[row];
 
-        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
@@ -588,7 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           rbase = p.resid + (size_t)rw0 * p.ldr + cbase;
           epi_resid_issue(rr, lane, rbase, p.ldr, rows_valid);
         }
-        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
@@ -800,7 +805,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       } else if constexpr (EPI == EPI_QKV) {
-        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
@@ -834,7 +839,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b = row_ok ? p.rowb[row] : -1;
         const int t = row - b * p.Lp;
         const float m = (b >= 0) ? p.rowmask[row] : 0.f;
-        if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
+        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();

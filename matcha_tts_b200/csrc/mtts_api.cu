@@ -196,6 +196,10 @@ struct MttsHandle {
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
+  bool pdl_late = true;  // MTTS_PDL_EARLY=1 restores griddepcontrol.launch_dependents at kernel entry.  Default: GEMM / tail / attention
+                         // CTAs release their dependents when their last accumulator is complete: dependents released at entry sit
+                         // on SM slots (shared memory, TMEM) that ready kernels of another chain / solve could use (+4.5% with three
+                         // solves in flight, +3% with one)
   // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
   // every kernel of a chain is small (tens of tiles) and latency-bound on its own
   int nsub_override = 0;  // MTTS_NSUB in the environment; 0 = heuristic
@@ -512,6 +516,7 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   pp.tl = nullptr;
   pp.w_hint = h->w_hint ? 1 : 0;
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
+  pp.pdl_late = h->pdl_late ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
                     wmap, pp));
@@ -680,7 +685,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
     AttnParams ap{};
     ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
-    ap.vt = H(w.vt); ap.out = H(w.o);
+    ap.vt = H(w.vt); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
     dim3 grid((lc.L + 127) / 128, 2, w.B);
     CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
     launched(h);
@@ -691,7 +696,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       TailParams tp{};
       tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
       tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
-      tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0;
+      tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
       tp.tl = h->tail_tl;
       const int tiles = (lc.rows + 127) / 128;
       const int grid = tiles < h->num_sms ? tiles : h->num_sms;
@@ -955,6 +960,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
   if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
