@@ -131,12 +131,16 @@ struct GemmParams {
 // KSUB = number of 64-column K chunks per pipeline stage.  KSUB = 2 needs the 3-D tensor maps ([nk][rows][64]
 // views, box {64, 128, 2}): one 32 KB TMA instruction per operand and stage -- a cp.async.bulk.tensor costs its
 // issuing thread ~330 cycles whatever the box size, which would cap the 256-cycle stage of a 128-wide N tile.
-template <int BN, int EPI = EPI_PLAIN, int KSUB = 1>
+// CG = 2: CTA pair (cluster of two, tcgen05 cta_group::2).  The pair computes a 256-row x BN tile; each CTA stages its
+// own 128 activation rows and HALF of the weight tile (BN/2 rows), so a stage is 32 KB instead of 48 KB: a third less
+// L2 -> shared-memory traffic per FLOP and six stages instead of four in flight (the 4 x 48 KB ring cannot cover the
+// TMA latency under load: 192 KB / ~1.5 us < the 185 GB/s one SM's MMA stream consumes).
+template <int BN, int EPI = EPI_PLAIN, int KSUB = 1, int CG = 1>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2 * KSUB;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2 * KSUB;
+  static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2 * KSUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (KSUB == 2 ? 3 : 4);
+  static constexpr int STAGES = (CG == 2) ? 6 : ((BN == 256) ? 4 : (KSUB == 2 ? 3 : 4));
   // per-column epilogue parameters of ALL n-tiles, staged once per CTA: [bias | p1 | p2] x PAR_N
   static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : (BN == 128 ? 512 : 1024);  // max N of one launch
   // GN variants: bias | res_bias | gn gamma | gn beta | ln gamma | ln beta, 256 floats each
@@ -201,12 +205,15 @@ __device__ __forceinline__ void epi_resid_add(uint32_t st, int lane, const uint4
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory"); }
 
-template <int BN, int EPI, int KSUB = 1>
+template <int BN, int EPI, int KSUB = 1, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using SM = GemmSmem<BN, EPI, KSUB>;
+  using SM = GemmSmem<BN, EPI, KSUB, CG>;
   static_assert(KSUB == 1 || (KSUB == 2 && BN == 128), "two K chunks per stage only for the 128-wide N tile");
+  static_assert(CG == 1 || (CG == 2 && BN == 256 && KSUB == 1 && (EPI == EPI_STATS || EPI == EPI_PLAIN)), "CTA pairs: 256-wide conv tiles");
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / accumulator-empty barriers both CTAs signal)
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int PN = SM::PAR_N;
   constexpr int STAGES = SM::STAGES;
   // accumulator stage stride: the STATS variant may feed a second accumulator (res_conv) per tile; with 128-wide tiles
@@ -242,23 +249,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   int total_chunks = 0;
   for (int s = 0; s < p.num_segs; ++s) total_chunks += p.seg[s].nchunks;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int total_tiles = m_tiles * p.n_tiles;
+  // a "unit" is what one CTA (CG = 1) or one CTA pair (CG = 2) works on: CG consecutive row tiles x one N tile
+  const int m_units = (m_tiles + CG - 1) / CG;
+  const int total_tiles = m_units * p.n_tiles;
+  const int unit0 = blockIdx.x / CG, nunits = gridDim.x / CG;
   // i-th tile of this CTA (or -1): round-robin over all tiles, or whole row tiles with their N tiles back to back
   auto cta_tile = [&](int i) -> int {
-    if (!p.m_major) { const int t = blockIdx.x + i * gridDim.x; return t < total_tiles ? t : -1; }
+    if (CG == 2 || !p.m_major) { const int t = unit0 + i * nunits; return t < total_tiles ? t : -1; }
     const int mt = blockIdx.x + (i / p.n_tiles) * gridDim.x;
     return mt < m_tiles ? mt * p.n_tiles + (i % p.n_tiles) : -1;
   };
+  // first row of this CTA inside unit tile `tile`
+  auto tile_r0 = [&](int tile) -> int { return ((tile / p.n_tiles) * CG + (int)crank) * GEMM_BM; };
 
   if (threadIdx.x == 0) {
+    // pair: the leader's full barrier counts the bytes of both CTAs' loads (its own two producers arrive and expect
+    // twice their bytes; the peer's TMA instructions complete_tx on it -- the transaction count may run negative inside
+    // a phase), its accumulator-empty barrier collects the epilogue warps of both CTAs; empty / accumulator-full
+    // barriers are signalled in both CTAs by multicast commits
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CG); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   // per-column epilogue parameters (weights: independent of the previous kernel) for every n-tile
   if (warp >= 3) {
     const int ncols = min(p.n_tiles * BN, PN);
@@ -272,7 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tl && threadIdx.x == 0) tl[1] = clock64();
@@ -288,6 +308,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&empty_bar[stage], phase ^ 1);   // converged warp; one elected lane issues
         if (elect_one()) {
           uint8_t* sb = smem + stage * SM::STAGE_BYTES + SM::A_BYTES;
+          if constexpr (CG == 2) {   // this CTA's half of the weight tile; bytes are counted on the leader's barrier
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::B_BYTES);
+            if (p.w_hint) tma_load_2d_pair_hint(sb, &tmB, lbar, kc * GEMM_BK, n0 + (int)crank * (BN / 2), pol);
+            else tma_load_2d_pair(sb, &tmB, lbar, kc * GEMM_BK, n0 + (int)crank * (BN / 2));
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], SM::B_BYTES);
           if constexpr (KSUB == 1) {
             if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
@@ -296,6 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (p.w_hint) tma_load_3d_hint(sb, &tmB, &full_bar[stage], 0, n0, kc, pol);
             else tma_load_3d(sb, &tmB, &full_bar[stage], 0, n0, kc);
           }
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -303,10 +330,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
 
-  if (KSUB == 1 && warp == 0 && (int)blockIdx.x < total_tiles && p.a_prefetch) {
+  if (KSUB == 1 && warp == 0 && cta_tile(0) >= 0 && p.a_prefetch) {
     // warm the TLB / L2 path of this CTA's first activation tiles while the previous kernel drains
     if (elect_one()) {
-      const int r0 = (cta_tile(0) / p.n_tiles) * GEMM_BM;
+      const int r0 = tile_r0(cta_tile(0));
       int kc = 0;
       for (int s = 0; s < p.num_segs && kc < STAGES; ++s) {
         const GemmSeg sg = p.seg[s];
@@ -330,27 +357,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
-      const int r0 = (tile / p.n_tiles) * GEMM_BM;
+      const int r0 = tile_r0(tile);
       for (int s = 0; s < p.num_segs; ++s) {
         const GemmSeg sg = p.seg[s];
         const CUtensorMap* tm = sg.src ? &tmA1 : &tmA0;
         for (int c = 0; c < sg.nchunks; c += KSUB) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
+            if constexpr (CG == 2) {
+              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::A_BYTES);
+              tma_load_2d_pair(smem + stage * SM::STAGE_BYTES, tm, lbar, sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
+            } else {
             mbar_arrive_expect_tx(&full_bar[stage], SM::A_BYTES);
             if constexpr (KSUB == 1)
               tma_load_2d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], sg.col0 + c * GEMM_BK, r0 + sg.row_shift);
             else
               tma_load_3d(smem + stage * SM::STAGE_BYTES, tm, &full_bar[stage], 0, r0 + sg.row_shift, sg.col0 / GEMM_BK + c);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN);
+  } else if (warp == 1 && crank == 0) {
+    // ===================================== MMA issuer (pair: the leader CTA only) ============
+    constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -374,10 +407,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int sub = 0; sub < KSUB; ++sub)   // K sub-chunk tiles are consecutive in the stage; descriptor address in 16-B units
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k)
+              if constexpr (CG == 2) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kc - kfirst) | k) != 0);
+              else
               umma_f16(d_tmem, da + sub * ((GEMM_BM * GEMM_BK * 2) >> 4) + 2 * k, db + sub * ((BN * GEMM_BK * 2) >> 4) + 2 * k, idesc,
                        ((kc - kfirst) | sub | k) != 0);
+          if constexpr (CG == 2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kc + KSUB >= total_chunks) umma_commit_pair(&tfull_bar[as]);
+          } else {
           umma_commit(&empty_bar[stage]);
           if (kc + KSUB >= total_chunks) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -400,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t aphase = 0;
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int n_tile = tile % p.n_tiles;
-      const int r0 = (tile / p.n_tiles) * GEMM_BM;
+      const int r0 = tile_r0(tile);
       const int n0 = n_tile * BN;
       const int rw0 = r0 + q * 32;       // first row of this warp
       const int row = rw0 + lane;        // my row
@@ -881,15 +921,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (!DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if constexpr (CG == 2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the last commit
+  else __syncthreads();
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
   if (tl && threadIdx.x == 0) { tl[7] = clock64(); tl[10] = (long long)globaltimer_ns(); }
 }
 

@@ -97,9 +97,12 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t n
 // {64, 128, 2} (two K chunks per TMA instruction; used by the 128-wide-N GEMM variant), when cols % 128 == 0.
 struct TMap {
   CUtensorMap d2, d3;
+  CUtensorMap d2h;   // 2-D with 128-row boxes: a CTA pair's half of a 256-row weight tile (cta_group::2 GEMMs)
 };
 static int make_tmap(TMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
   if (make_map(&m->d2, base, rows, cols, pitch, box_rows)) return MTTS_ECUDA;
+  m->d2h = m->d2;
+  if (box_rows == 256 && make_map(&m->d2h, base, rows, cols, pitch, 128)) return MTTS_ECUDA;
   m->d3 = m->d2;
   if (cols % 128 == 0 && make_map3(&m->d3, base, rows, (uint32_t)(cols / 64), pitch, 128, 2)) return MTTS_ECUDA;
   return 0;
@@ -196,6 +199,7 @@ struct MttsHandle {
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
+  bool cta_pairs = true; // MTTS_NO_PAIRS=1: 256-wide conv GEMMs on single CTAs (cta_group::1) instead of CTA pairs (cta_group::2)
   bool pdl_late = true;  // MTTS_PDL_EARLY=1 restores griddepcontrol.launch_dependents at kernel entry.  Default: GEMM / tail / attention
                          // CTAs release their dependents when their last accumulator is complete: dependents released at entry sit
                          // on SM slots (shared memory, TMEM) that ready kernels of another chain / solve could use (+4.5% with three
@@ -497,6 +501,30 @@ static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 gr
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// CTA-pair launch: cluster of 2 (+ programmatic stream serialization like launch_k)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k_pair(const MttsHandle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (h->use_pdl && !h->profiling && !h->pdl_break) ? 2 : 1;
+  h->pdl_break = false;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+template <int EPI>
+static int set_gemm_pair_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<256, EPI, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<256, EPI, 1, 2>::TOTAL));
+  return 0;
+}
+
 template <int BN, int EPI, int KSUB = 1>
 static int set_gemm_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -533,6 +561,21 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
       if ((p.seg[i].nchunks & 1) || ((p.seg[i].col0 / 64) & 1)) return fail(MTTS_EINVAL, "128-wide N tile needs whole 128-column K pairs");
     return launch_gemm_maps<128, EPI, 2>(h, a0.d3, a1.d3, wmap.d3, p, stream, aflops);
   } else {
+    if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
+      if (h->cta_pairs) {   // tcgen05 cta_group::2: a CTA pair per 256-row tile, each CTA staging half of the weight tile
+        if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
+        const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+        const int units = ((m_tiles + 1) / 2) * p.n_tiles;
+        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+        GemmParams pp = p;
+        pp.tl = nullptr; pp.m_major = 0;
+        pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
+        CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
+                               stream, a0.d2, a1.d2, wmap.d2h, pp));
+        launched(h);
+        return 0;
+      }
+    }
     return launch_gemm_maps<BN, EPI, 1>(h, a0.d2, a1.d2, wmap.d2, p, stream, aflops);
   }
 }
@@ -961,6 +1004,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_NO_PAIRS")) h->cta_pairs = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
   if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
@@ -986,6 +1030,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     h->num_sms = prop.multiProcessorCount;
     int e = 0;
     e |= set_gemm_attr<256, EPI_GNA>(); e |= set_gemm_attr<256, EPI_GNB>();
+    e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
     e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
     e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
@@ -1370,9 +1415,10 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
   h->launch_limit = -1;
   int e;
   if (N % 256 == 0) {
-    if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 256)) return MTTS_ECUDA;
+    TMap ta, tw;   // production 256-wide path (CTA pairs unless MTTS_NO_PAIRS=1)
+    if (make_tmap(&ta, A, rows, C, C, 128) || make_tmap(&tw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 256)) return MTTS_ECUDA;
     p.n_tiles = N / 256;
-    e = launch_gemm_maps<256, EPI_PLAIN, 1>(h, ma, ma, mw, p, stream, 0.0);
+    e = launch_gemm<256, EPI_PLAIN>(h, ta, ta, tw, p, stream);
   } else if (C % 128 == 0) {   // production 128-wide path: two K chunks per stage through the 3-D maps
     TMap ta, tw;
     if (make_tmap(&ta, A, rows, C, C, 128) || make_tmap(&tw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;

@@ -20,7 +20,7 @@ def main():
     reps = 200
     print("rows   C    N   taps | us/launch   GFLOP   TFLOP/s")
     shapes = ((256, 256, 1), (256, 256, 3)) if os.environ.get("MTTS_DBG") else ((256, 256, 1), (256, 256, 3), (512, 256, 3), (256, 128, 1), (256, 384, 1))
-    for rows in (128, 11072):
+    for rows in (128, 11072, 88576):
         for Cc, N, taps in shapes:
             A = torch.randn(rows, Cc, device=dev).half()
             W = torch.randn(N, taps * Cc, device=dev).half()
