@@ -108,7 +108,8 @@ struct GemmParams {
   // EPI_QKV
   __half* q;
   __half* k;
-  __half* vt;  // [(b*2+h)*64 + d][Lpad]
+  __half* vt;  // [(b*2+h)*64 + d][Lpad]  (first-generation attention kernel)
+  __half* v;   // [rows][128] row-major like q / k (attention2.cuh); when set, vt is not written
   int Lpad;
   // EPI_FINAL
   float* zout;         // (B, n_valid, T) channels-first fp32
@@ -849,8 +850,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
-        if (n_tile < 2) {
-          __half* dst = (n_tile == 0 ? p.q : p.k) + (size_t)rw0 * BN + cbase;
+        if (n_tile < 2 || p.v != nullptr) {
+          __half* dst = (n_tile == 0 ? p.q : (n_tile == 1 ? p.k : p.v)) + (size_t)rw0 * BN + cbase;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             float v[32];

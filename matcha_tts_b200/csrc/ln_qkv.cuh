@@ -37,6 +37,7 @@ struct LnQkvParams {
   __half* q;                // [rows, 128]
   __half* k;                // [rows, 128]
   __half* vt;               // [(b*2+h)*64 + d][Lpad]
+  __half* v;                // [rows, 128] row-major (attention2.cuh); when set, vt is not written
   int Lpad;
   int w_hint;
 };
@@ -255,8 +256,8 @@ ln_qkv_kernel(const __grid_constant__ CUtensorMap tmW3, const LnQkvParams p) {
         float v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (col < 256) {
-          __half* dst = (col < 128 ? p.q : p.k) + (size_t)rw0 * 128 + (col & 127);
+        if (col < 256 || p.v != nullptr) {
+          __half* dst = (col < 128 ? p.q : (col < 256 ? p.k : p.v)) + (size_t)rw0 * 128 + (col & 127);
           epi_store_h32(st, lane, v, dst, 128, rows_valid);
         } else if (b >= 0) {
           const int cc = col - 256;         // head cc/64, dim cc%64; lanes = consecutive frames

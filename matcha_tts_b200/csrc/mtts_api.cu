@@ -15,6 +15,7 @@
 
 #include "../../include/mtts.h"
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
 #include "gemm_tc.cuh"
@@ -142,7 +143,7 @@ struct StageW {
 struct WsLayout {
   int B, T, H, LpT, LpH, rowsT, rowsH, LpadT, LpadH, S, cinp, nt_max;
   size_t maskT, maskH, rowbT, rowbH, npadT, npadH, tvals, te_e, te_h1, te_h2, te6, part;
-  size_t x0, y, res, h1, xr, a, xa, q, k, o, vt, s;
+  size_t x0, y, res, h1, xr, a, xa, q, k, o, vt, v, s;
   size_t skip0, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF, zmid;
   size_t flags;   // two arrays of nflags ints: inter-CTA flags of the fused GroupNorm conv launches (ping-pong)
   int nflags;
@@ -152,6 +153,8 @@ struct WsLayout {
 struct LevelMaps {
   TMap h1, a;
   CUtensorMap o, s, q, k, vt;
+  CUtensorMap k2, v2;  // attention2.cuh: k / v [rows][128] with KT-row boxes
+  int KT, nkv;         // keys per tile (multiple of 16, <= 192) and tiles per utterance
   CUtensorMap o3;  // o as [2][rows][64], box {64, 128, 2} (fused tail)
 };
 struct Plan {
@@ -199,6 +202,7 @@ struct MttsHandle {
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
+  bool attn_v2 = true;   // MTTS_ATTN_V1=1: first-generation attention kernel (128-key tiles, V transposed by the QKV epilogue)
   bool cta_pairs = true; // MTTS_NO_PAIRS=1: 256-wide conv GEMMs on single CTAs (cta_group::1) instead of CTA pairs (cta_group::2)
   bool pdl_late = true;  // MTTS_PDL_EARLY=1 restores griddepcontrol.launch_dependents at kernel entry.  Default: GEMM / tail / attention
                          // CTAs release their dependents when their last accumulator is complete: dependents released at entry sit
@@ -403,6 +407,7 @@ static bool ws_layout(const MttsHandle* h, int B, int T, WsLayout* w) {
   w->q = alloc(2 * rT * 128); w->k = alloc(2 * rT * 128); w->o = alloc(2 * rT * 128);
   w->vt_bytes = 2ull * B * 128 * w->LpadT;
   w->vt = alloc(w->vt_bytes);
+  w->v = alloc(2 * rT * 128);
   w->s = alloc(2 * rT * 4 * C);
   w->skip0 = alloc(2 * rT * C); w->xD0 = alloc(2 * rH * C); w->skip1 = alloc(2 * rH * C); w->xD1 = alloc(2 * rH * C);
   w->xM0 = alloc(2 * rH * C); w->xM1 = alloc(2 * rH * C); w->xU0s = alloc(2 * rH * C);
@@ -439,6 +444,11 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
     if (make_map(&m.q, b + w.q, rows, 128, 128, 128)) return MTTS_ECUDA;
     if (make_map(&m.k, b + w.k, rows, 128, 128, 128)) return MTTS_ECUDA;
     if (make_map(&m.vt, b + w.vt, (uint64_t)B * 128, Lpad, Lpad, 64)) return MTTS_ECUDA;
+    const int L = lv ? w.H : w.T;
+    m.nkv = (L + ATT2_KT_MAX - 1) / ATT2_KT_MAX;
+    m.KT = (int)align_up((L + m.nkv - 1) / m.nkv, 16);
+    if (make_map(&m.k2, b + w.k, rows, 128, 128, m.KT)) return MTTS_ECUDA;
+    if (make_map(&m.v2, b + w.v, rows, 128, 128, m.KT)) return MTTS_ECUDA;
   }
   const uint64_t rT = w.rowsT, rH = w.rowsH;
   if (make_tmap(&P.x0, b + w.x0, rT, w.cinp, w.cinp, 128)) return MTTS_ECUDA;
@@ -691,7 +701,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     // q | k | v^T
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
-    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
+    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.v = h->attn_v2 ? H(w.v) : nullptr; p.Lpad = lc.Lpad;
     if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
   } else if (h->fused_lnqkv && h->fused_tail) {
     // x_r = Mish(GN(y))*m + res ; a = LN1(x_r) (on chip) ; q | k | v^T = a Wqkv^T   -- one kernel
@@ -701,7 +711,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       lp.y = H(w.y); lp.res = H(w.res); lp.stats_part = part;
       lp.gamma = F(sw.gn2_g); lp.beta = F(sw.gn2_b); lp.ln_g = F(sw.ln1_g); lp.ln_b = F(sw.ln1_b);
       lp.rowmask = lc.mask; lp.rowb = lc.rowb; lp.xr = H(w.xr);
-      lp.q = H(w.q); lp.k = H(w.k); lp.vt = H(w.vt); lp.Lpad = lc.Lpad; lp.w_hint = h->w_hint ? 1 : 0;
+      lp.q = H(w.q); lp.k = H(w.k); lp.vt = H(w.vt); lp.v = h->attn_v2 ? H(w.v) : nullptr; lp.Lpad = lc.Lpad; lp.w_hint = h->w_hint ? 1 : 0;
       const int tiles = (lc.rows + 127) / 128;
       const int grid = tiles < h->num_sms ? tiles : h->num_sms;
       CUDA_TRY(launch_k(h, ln_qkv_kernel, dim3(grid), dim3(LQ_THREADS), LQ_SMEM, stream, sw.m_qkv.d3, lp));
@@ -720,17 +730,24 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     {
       GemmParams p = base;
       segs_taps(p, 1, kTap1, C, 0);
-      p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.Lpad = lc.Lpad;
+      p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.v = h->attn_v2 ? H(w.v) : nullptr; p.Lpad = lc.Lpad;
       if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
     }
   }
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
-    AttnParams ap{};
-    ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
-    ap.vt = H(w.vt); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
     dim3 grid((lc.L + 127) / 128, 2, w.B);
-    CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
+    if (h->attn_v2) {
+      Attn2Params ap{};
+      ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
+      ap.v = H(w.v); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
+      CUDA_TRY(launch_k(h, attention2_kernel, grid, dim3(ATT2_THREADS), ATT2_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
+    } else {
+      AttnParams ap{};
+      ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
+      ap.vt = H(w.vt); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
+      CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
+    }
     launched(h);
   }
   if (h->fused_tail) {
@@ -1005,6 +1022,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_PAIRS")) h->cta_pairs = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_ATTN_V1")) h->attn_v2 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
   if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
@@ -1035,6 +1053,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
     e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ln_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
@@ -1393,7 +1412,7 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
       {"npadH", w.npadH}, {"tvals", w.tvals}, {"te_e", w.te_e},   {"te_h1", w.te_h1}, {"te_h2", w.te_h2},
       {"te6", w.te6},     {"part", w.part},   {"x0", w.x0},       {"y", w.y},         {"res", w.res},
       {"h1", w.h1},       {"xr", w.xr},       {"a", w.a},         {"xa", w.xa},       {"q", w.q},
-      {"k", w.k},         {"o", w.o},         {"vt", w.vt},       {"s", w.s},         {"skip0", w.skip0},
+      {"k", w.k},         {"o", w.o},         {"vt", w.vt},       {"v", w.v},       {"s", w.s},         {"skip0", w.skip0},
       {"xD0", w.xD0},     {"skip1", w.skip1}, {"xD1", w.xD1},     {"xM0", w.xM0},     {"xM1", w.xM1},
       {"xU0s", w.xU0s},   {"xU0", w.xU0},     {"xU1s", w.xU1s},   {"xF", w.xF},       {"zmid", w.zmid}};
   auto it = m.find(name);
