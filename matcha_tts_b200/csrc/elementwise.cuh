@@ -102,7 +102,6 @@ constexpr int GN_ROWS_PER_BLOCK = 16; // 4 rows per warp, all in flight at once
 
 template <int MODE>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) {
-  __shared__ float s_mean[8], s_rstd[8];
   pdl_launch_dependents();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,33 +146,24 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
     const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
     te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
   }
-  // 2) finalise the GroupNorm statistics of utterance b: 16 threads per group sum the per-32-row
-  //    partials in a fixed order (deterministic), in double to keep E[x^2]-E[x]^2 safe
+  // 2) finalise the GroupNorm statistics of utterance b: the 4 lanes that share a group sum its per-32-row partials
+  //    in a fixed order (deterministic) and combine by shuffles -- per warp, no shared memory, no block barrier.
+  //    fp32 is enough: the partials are fp32 sums already and |mean| is O(std) for these conv outputs.
+  float mean, rstd;
   {
-    const int gg = threadIdx.x >> 4, k = threadIdx.x & 15;
     const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
-    double s = 0.0, ss = 0.0;
-    for (int sl = k; sl <= last - first; sl += 16) {
-      const float2 pp = *reinterpret_cast<const float2*>(p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * gg);
-      s += (double)pp.x;
-      ss += (double)pp.y;
+    float s = 0.f, ss = 0.f;
+    for (int sl = lane & 3; sl <= last - first; sl += 4) {
+      const float2 pp = *reinterpret_cast<const float2*>(p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * g);
+      s += pp.x;
+      ss += pp.y;
     }
-#pragma unroll
-    for (int off = 8; off > 0; off >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, off);
-      ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    }
-    if (k == 0) {
-      const double n = 32.0 * (double)p.L;
-      const double mean = s / n;
-      double var = ss / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean[gg] = (float)mean;
-      s_rstd[gg] = (float)(1.0 / sqrt(var + 1e-5));
-    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float inv_n = 1.f / (32.f * (float)p.L);
+    mean = s * inv_n;
+    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ss * inv_n), 0.f) + 1e-5f);
   }
-  __syncthreads();
-  const float mean = s_mean[g], rstd = s_rstd[g];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     ga[j] *= rstd;

@@ -203,7 +203,9 @@ struct MttsHandle {
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   bool attn_v2 = true;   // MTTS_ATTN_V1=1: first-generation attention kernel (128-key tiles, V transposed by the QKV epilogue)
-  bool cta_pairs = true; // MTTS_NO_PAIRS=1: 256-wide conv GEMMs on single CTAs (cta_group::1) instead of CTA pairs (cta_group::2)
+  int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
+  bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
+                          // pair launches measured -1% (4.57 vs 4.63 M frames/s) although the kernel alone gains 5-10% at full occupancy
   bool pdl_late = true;  // MTTS_PDL_EARLY=1 restores griddepcontrol.launch_dependents at kernel entry.  Default: GEMM / tail / attention
                          // CTAs release their dependents when their last accumulator is complete: dependents released at entry sit
                          // on SM slots (shared memory, TMEM) that ready kernels of another chain / solve could use (+4.5% with three
@@ -572,7 +574,11 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
     return launch_gemm_maps<128, EPI, 2>(h, a0.d3, a1.d3, wmap.d3, p, stream, aflops);
   } else {
     if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
-      if (h->cta_pairs) {   // tcgen05 cta_group::2: a CTA pair per 256-row tile, each CTA staging half of the weight tile
+      int chunks = 0;
+      for (int i = 0; i < p.num_segs; ++i) chunks += p.seg[i].nchunks;
+      // tcgen05 cta_group::2: a CTA pair per 256-row tile, each CTA staging half of the weight tile.  Pays off for long K
+      // (tools/gemm_repeat.py at 692 row tiles: K=1536 1221 vs 1111 TFLOP/s, K=768 1090 vs 1035, K=256 518 vs 597)
+      if (h->cta_pairs && chunks >= h->pair_min_chunks) {
         if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
         const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
         const int units = ((m_tiles + 1) / 2) * p.n_tiles;
@@ -1021,8 +1027,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_NO_PAIRS")) h->cta_pairs = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_PAIRS")) h->cta_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_ATTN_V1")) h->attn_v2 = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
   if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;

@@ -45,7 +45,10 @@ def _d(x):
 ])
 def test_gemm_tc(lj, rows, Cc, N, shifts):
     dec, _, _ = lj
-    eng = dec._engine(torch.device("cuda", 0))
+    _check_gemm(dec._engine(torch.device("cuda", 0)), rows, Cc, N, shifts)
+
+
+def _check_gemm(eng, rows, Cc, N, shifts):
     g = torch.Generator().manual_seed(rows + N)
     A = torch.randn(rows, Cc, generator=g).half().cuda()
     W = (torch.randn(N, len(shifts) * Cc, generator=g) / (len(shifts) * Cc) ** 0.5).half().cuda()
@@ -341,10 +344,13 @@ def test_chains_setting_keeps_results(lj):
 # ---------------------------------------------------------------------------------------------
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env", ["MTTS_GNFUSE", "MTTS_LNQKV", "MTTS_STAGGER", "MTTS_NO_TAIL", "MTTS_NO_PDL"])
+@pytest.mark.parametrize("env", ["MTTS_GNFUSE", "MTTS_LNQKV", "MTTS_STAGGER", "MTTS_NO_TAIL", "MTTS_NO_PDL", "MTTS_PAIRS",
+                                 "MTTS_ATTN_V1", "MTTS_PDL_EARLY"])
 def test_opt_in_variants(env):
     old = os.environ.get(env)
     os.environ[env] = "1"
+    if env == "MTTS_PAIRS":
+        os.environ["MTTS_PAIR_MIN_CHUNKS"] = "0"
     if env == "MTTS_STAGGER":
         os.environ["MTTS_NSUB"] = "2"
     try:
@@ -355,8 +361,13 @@ def test_opt_in_variants(env):
             z = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "euler", use_graph=use_graph).cpu()
             ma, rl = O.parity_errors(z, zr, mask)
             assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (env, use_graph, ma, rl)
+        if env == "MTTS_PAIRS":      # the unit GEMM through the CTA-pair kernel: odd tile counts, several N tiles
+            eng = dec._engine(torch.device("cuda", 0))
+            for rows, Cc, N, shifts in [(129, 256, 256, [-1, 0, 1]), (5000, 256, 1024, [0]), (777, 512, 512, [-1, 0, 1])]:
+                _check_gemm(eng, rows, Cc, N, shifts)
     finally:
         os.environ.pop("MTTS_NSUB", None)
+        os.environ.pop("MTTS_PAIR_MIN_CHUNKS", None)
         if old is None:
             os.environ.pop(env, None)
         else:
