@@ -394,9 +394,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const int rc0 = (epi_has_stats(EPI) && p.res_chunk0 > 0) ? p.res_chunk0 : total_chunks;  // dual: both TMEM halves
+      // dual accumulators in one 256-wide TMEM stage: the two halves are handed over separately -- barrier pair [0] for
+      // the conv accumulator (complete after chunk rc0-1, free once y / the statistics are out), pair [1] for the
+      // res_conv accumulator (complete at the end, free once res is out) -- so the epilogue drains the conv half while
+      // the res chunks run and the next tile's conv chunks run while the res half drains
+      const bool dual_split = !DUAL_DOUBLE && rc0 < total_chunks;
       for (int kc = 0; kc < total_chunks; kc += KSUB) {
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE + ((kc >= rc0) ? BN : 0);
         const int kfirst = (kc >= rc0) ? rc0 : 0;
+        if (dual_split && kc == rc0) { mbar_wait(&tempty_bar[1], aphase ^ 1); tc_fence_after(); }
         mbar_wait(&full_bar[stage], phase);
         if (tl && lane == 0 && kc == 0 && ti == 0) tl[3] = clock64();
         tc_fence_after();
@@ -414,10 +420,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                        ((kc - kfirst) | sub | k) != 0);
           if constexpr (CG == 2) {
             umma_commit_pair(&empty_bar[stage]);
-            if (kc + KSUB >= total_chunks) umma_commit_pair(&tfull_bar[as]);
+            if (dual_split && kc + KSUB == rc0) umma_commit_pair(&tfull_bar[0]);
+            if (kc + KSUB >= total_chunks) umma_commit_pair(&tfull_bar[dual_split ? 1 : as]);
           } else {
           umma_commit(&empty_bar[stage]);
-          if (kc + KSUB >= total_chunks) umma_commit(&tfull_bar[as]);
+          if (dual_split && kc + KSUB == rc0) umma_commit(&tfull_bar[0]);
+          if (kc + KSUB >= total_chunks) umma_commit(&tfull_bar[dual_split ? 1 : as]);
           }
         }
         __syncwarp();
@@ -565,6 +573,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[14] = clock64();
         if constexpr (EPI == EPI_STATS) {
           if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
+            if constexpr (!DUAL_DOUBLE) {   // hand the conv half back, then wait for the res half (see the MMA warp)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[0]), 0));
+                else mbar_arrive(&tempty_bar[0]);
+                mbar_wait(&tfull_bar[1], aphase);
+              }
+              __syncwarp();
+              tc_fence_after();
+            }
             __half* rob = p.res_out + (size_t)rw0 * p.ldo + n0 + cbase;
             tmem_ld32(taddr + BN, vbuf[0]);
 #pragma unroll
@@ -714,6 +733,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         // meanwhile: the second accumulator (res_conv) / the time-embedding rows of the tile's utterances
         if (p.res_chunk0 > 0) {
+          if (lane == 0) mbar_wait(&tfull_bar[1], aphase);   // the res half completes after the conv half (see the MMA warp)
+          __syncwarp();
+          tc_fence_after();
           __half* rob = p.res_out + (size_t)rw0 * p.ldo + cbase;
           float vbuf[2][32];
           tmem_ld32(taddr + BN, vbuf[0]);
@@ -922,11 +944,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      const bool dual_split = !DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0;
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(&tempty_bar[as]);
+        // dual_split: EPI_STATS released the conv half above and releases the res half here; the fused-GroupNorm
+        // epilogues hold both halves to the end
+        if (dual_split && epi_is_gn(EPI)) {
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[0]), 0));
+          else mbar_arrive(&tempty_bar[0]);
+        }
+        uint64_t* eb = &tempty_bar[dual_split ? 1 : as];
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(eb), 0));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(eb);
       }
-      if (!DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
+      if (dual_split) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
   }
