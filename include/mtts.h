@@ -79,6 +79,12 @@ int mtts_weights_loaded(const MttsHandle* h); /* 1 when every table entry has be
  * Returns 0 on invalid shapes. */
 size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T);
 
+/* Forget everything cached for a workspace the caller is about to free or reuse for something else (the per-shape plan
+ * with its tensor maps, and the CUDA graphs captured over it).  The library zero-fills a workspace once, when it first
+ * sees the (pointer, B, T) triple, and relies on its guard rows staying zero afterwards: a caller that recycles
+ * workspace memory must call this before handing the same address back.  Work already enqueued must have completed. */
+int mtts_release_workspace(MttsHandle* h, const void* workspace, size_t workspace_bytes);
+
 /* ---- compute ------------------------------------------------------------------------------- */
 /* One estimator call: out = Decoder.forward(x, mask, mu, t, spks)     (reference model.py:964) */
 int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const float* mask, const float* t,

@@ -90,6 +90,15 @@ def pad_batch(mus: Sequence[torch.Tensor], bucket: Bucket, device=None):
     """Stack the (n_feats, T_i) encoder outputs of a bucket into (B, n_feats, T_max) + prefix mask."""
     n_feats = mus[bucket.indices[0]].shape[0]
     B = len(bucket.indices)
+    first = mus[bucket.indices[0]]
+    if first.is_cuda and (device is None or torch.device(device) == first.device):
+        # encoder outputs already on the GPU: one padding kernel instead of 2*B small copies
+        seqs = [mus[i].to(torch.float32).t() for i in bucket.indices]                      # (T_i, n_feats)
+        seqs.append(first.new_zeros(bucket.t_max, n_feats, dtype=torch.float32))           # forces T_max
+        mu = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)[:B].permute(0, 2, 1).contiguous()
+        lens = torch.tensor([mus[i].shape[1] for i in bucket.indices], device=first.device)
+        mask = (torch.arange(bucket.t_max, device=first.device)[None, :] < lens[:, None]).unsqueeze(1).float()
+        return mu, mask
     mu = torch.zeros(B, n_feats, bucket.t_max, dtype=torch.float32, device=device)
     mask = torch.zeros(B, 1, bucket.t_max, dtype=torch.float32, device=device)
     for row, i in enumerate(bucket.indices):
@@ -99,12 +108,22 @@ def pad_batch(mus: Sequence[torch.Tensor], bucket: Bucket, device=None):
     return mu, mask
 
 
+_PINNED: Dict[tuple, List[torch.Tensor]] = {}     # recycled pinned host buffers (cudaHostAlloc is slow and synchronising)
+
+
+def _pinned(shape: tuple) -> torch.Tensor:
+    free = _PINNED.get(shape)
+    if free:
+        return free.pop()
+    return torch.empty(shape, dtype=torch.float32, pin_memory=True)
+
+
 Solver = Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Bucket], torch.Tensor]
 
 
 def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Sequence[torch.Tensor]] = None,
                   max_frames: int = 64 * 344, max_batch: int = 256, device=None, group=None,
-                  gather: bool = True) -> Dict[int, torch.Tensor]:
+                  gather: bool = True, lanes: int = 1) -> Dict[int, torch.Tensor]:
     """Run `solver(mu, mask, spks, bucket) -> (B, n_feats, T_max)` over this rank's buckets and gather.
 
     mus[i]: (n_feats, T_i) encoder output of utterance i (every rank passes the same list; only the
@@ -112,6 +131,8 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
     `gather` every rank gets all utterances, otherwise only its own.
     In production `solver` is `lambda mu, mask, s, b: cfm(mu, mask, n_timesteps, temperature, s)`
     (matcha_tts_b200.CFM); the CPU tests inject a stub, the scheduling/gather logic is the same.
+    `lanes` > 1 (CUDA only) keeps that many buckets in flight on as many CUDA streams -- every stream has its own
+    native engine, so consecutive solves overlap on the GPU -- and copies the mels to pinned host memory asynchronously.
     """
     import torch.distributed as dist
     use_dist = dist.is_available() and dist.is_initialized()
@@ -121,16 +142,49 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
     buckets = make_buckets(lengths, max_frames, max_batch)
     mine = assign_buckets(buckets, world)[rank]
     local: Dict[int, torch.Tensor] = {}
-    for bid in mine:
-        bk = buckets[bid]
-        mu, mask = pad_batch(mus, bk, device)
-        s = None
-        if spks is not None:
-            s = torch.stack([spks[i] for i in bk.indices]).to(device=device, dtype=torch.float32)
-        out = solver(mu, mask, s, bk)
-        out = out.detach().to("cpu", torch.float32)
+
+    def unpack(bk, out):
         for row, i in enumerate(bk.indices):
             local[i] = out[row, :, :lengths[i]].clone()
+
+    dev = torch.device(device) if device is not None else None
+    if lanes > 1 and dev is not None and dev.type == "cuda":
+        streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
+        cur = torch.cuda.current_stream(dev)
+        pending = []                                   # (bucket, pinned host mel, event, device mel kept alive)
+        for k, bid in enumerate(mine):
+            bk = buckets[bid]
+            ls = streams[k % lanes]
+            ls.wait_stream(cur)
+            with torch.cuda.stream(ls):
+                mu, mask = pad_batch(mus, bk, dev)
+                s = None
+                if spks is not None:
+                    s = torch.stack([spks[i] for i in bk.indices]).to(device=dev, dtype=torch.float32)
+                out = solver(mu, mask, s, bk).detach()
+                host = _pinned(tuple(out.shape))
+                host.copy_(out, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(ls)
+            pending.append((bk, host, ev, out))
+            while len(pending) > 2 * lanes:            # bound the queue: finish the oldest bucket
+                b0, h0, e0, _ = pending.pop(0)
+                e0.synchronize()
+                unpack(b0, h0)
+                _PINNED.setdefault(tuple(h0.shape), []).append(h0)
+        for b0, h0, e0, _ in pending:
+            e0.synchronize()
+            unpack(b0, h0)
+            _PINNED.setdefault(tuple(h0.shape), []).append(h0)
+    else:
+        for bid in mine:
+            bk = buckets[bid]
+            mu, mask = pad_batch(mus, bk, device)
+            s = None
+            if spks is not None:
+                s = torch.stack([spks[i] for i in bk.indices]).to(device=device, dtype=torch.float32)
+            out = solver(mu, mask, s, bk)
+            unpack(bk, out.detach().to("cpu", torch.float32))
     if not (use_dist and gather and world > 1):
         return local
     parts: List[Optional[dict]] = [None] * world

@@ -1351,6 +1351,23 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
   return 0;
 }
 
+int mtts_release_workspace(MttsHandle* h, const void* workspace, size_t workspace_bytes) {
+  if (!h || !workspace) return fail(MTTS_EINVAL, "null argument");
+  const char* lo = static_cast<const char*>(workspace);
+  const char* hi = lo + workspace_bytes;
+  for (auto it = h->plans.begin(); it != h->plans.end();) {
+    const char* w = static_cast<const char*>(std::get<0>(it->first));
+    if (w >= lo && w < hi) it = h->plans.erase(it);
+    else ++it;
+  }
+  for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+    const char* w = static_cast<const char*>(it->first.ws);
+    if (w >= lo && w < hi) { cudaGraphExecDestroy(it->second.first); it = h->graphs.erase(it); }
+    else ++it;
+  }
+  return 0;
+}
+
 int mtts_set_chains(MttsHandle* h, int n) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
   if (n < 0 || n > 8) return fail(MTTS_EINVAL, "chains must be in [0, 8]");

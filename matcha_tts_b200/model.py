@@ -169,15 +169,29 @@ class _Engine:
         self.ws.clear()
         self.static.clear()
 
+    MAX_SHAPES = 24     # workspaces (and static graph buffers) kept per engine; least recently used shapes are dropped
+
     def workspace(self, B: int, T: int):
         key = (B, T)
         if key not in self.ws:
             n = self.lib.mtts_workspace_bytes(self.h, B, T)
             if n == 0:
                 raise _lib.MttsError(f"unsupported shape B={B}, T={T}: T must be even and >= 2")
+            while len(self.ws) >= self.MAX_SHAPES:           # bucketed serving sees many (B, T): bound the memory
+                old = next(iter(self.ws))
+                self._drop_shape(old)
             buf, ptr = _aligned_buffer(n, self.device, 1024)
             self.ws[key] = (buf, ptr, n)
+        else:
+            self.ws[key] = self.ws.pop(key)                  # most recently used last
         return self.ws[key]
+
+    def _drop_shape(self, key):
+        buf, ptr, n = self.ws.pop(key)
+        torch.cuda.synchronize(self.device)                   # nothing enqueued may still use it
+        _lib.check(self.lib.mtts_release_workspace(self.h, ptr, n))
+        for sk in [k for k in self.static if k[:2] == key]:
+            del self.static[sk]
 
     def estimator(self, x, mu, mask, t, spks, out):
         B, _, T = x.shape
@@ -232,7 +246,8 @@ class _Engine:
     def set_chains(self, n: int):
         """Utterance chains per solve (0 = heuristic; 1 when several solves are kept in flight on several streams)."""
         _lib.check(self.lib.mtts_set_chains(self.h, int(n)))
-        self.ws.clear()            # the workspace size depends on the chain layout
+        for key in list(self.ws):  # the workspace size depends on the chain layout
+            self._drop_shape(key)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,71 @@
+"""BASELINE config 5: multi-speaker (VCTK-shape, in_channels 224) decoder, 4096 utterances with clipped log-normal
+lengths, length-bucketed and sharded over the ranks of one node (one process per GPU, no hot-path collective).
+    python tools/config5.py [n_utt]                                  (1 GPU)
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/config5.py [n_utt]
+Prints one JSON line: valid and padded mel-frames/s of the whole job (bucketing, padding, solves on 3 lanes, D2H)."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from matcha_tts_b200 import CFM, Decoder, batching  # noqa: E402
+
+
+def main():
+    n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    g = torch.Generator().manual_seed(6)
+    lengths = torch.exp(torch.randn(n_utt, generator=g) * 0.45 + 5.7).clamp(64, 800).long().tolist()   # median ~300
+    torch.manual_seed(0)
+    dec = Decoder(in_channels=224, out_channels=80, channels=(256, 256), num_heads=2, num_mid_blocks=2).to(dev)
+    dec.set_chains(1)
+    cfm = CFM(80, {"solver": "euler", "sigma_min": 1e-4}, n_spks=109, spk_emb_dim=64, estimator=dec)
+    gd = torch.Generator(device=dev).manual_seed(5)
+    mus = [torch.randn(80, n, generator=gd, device=dev) for n in lengths]
+    spks = [torch.randn(64, generator=gd, device=dev) for _ in lengths]
+    buckets = batching.make_buckets(lengths)
+    mine = batching.assign_buckets(buckets, world)[rank]
+
+    def solver(mu, mask, s, bk):
+        return cfm(mu, mask, 10, temperature=0.667, spks=s)
+
+    def run():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = batching.solve_sharded(mus, solver, spks, device=dev, gather=False, lanes=3)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, out
+
+    run()                                   # warm-up: captures one CUDA graph per (lane, bucket shape)
+    if world > 1:
+        torch.distributed.barrier()
+    dt, out = run()
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        valid = sum(lengths)
+        padded = sum(b.padded_frames for b in buckets)
+        print(json.dumps({"config": "BASELINE configs[4]: VCTK-shape decoder, %d utterances, lengths clipped log-normal "
+                                    "[64, 800] median %d, bucketed (<= 64*344 padded frames per batch), 3 solve lanes per GPU" %
+                                    (n_utt, sorted(lengths)[n_utt // 2]),
+                          "n_gpus": world, "buckets": len(buckets), "buckets_rank0": len(mine), "seconds": dt,
+                          "valid_frames_per_s": valid / dt, "padded_frames_per_s": padded / dt,
+                          "padding_overhead": padded / valid - 1.0, "finite": bool(all(torch.isfinite(v).all() for v in out.values()))}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
