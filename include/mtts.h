@@ -130,6 +130,8 @@ int mtts_debug_set_tail_timeline(MttsHandle* h, void* dev_buf);
 
 /* ---- introspection used by the parity tests -------------------------------------------------- */
 /* Stop the estimator after `n` kernel launches (n < 0: run everything). */
+/* Per-tile stamps of the following GEMM launches (tools/gemm_tiles.py): dev_buf = [148][64] int64, or NULL to stop. */
+int mtts_debug_set_tile_timeline(MttsHandle* h, void* dev_buf);
 int mtts_debug_set_launch_limit(MttsHandle* h, int n);
 /* Byte offset / row count / column count of a named intermediate inside the workspace for (B, T);
  * level 0 = T frames, 1 = T/2 frames.  Returns -1 for an unknown name. */

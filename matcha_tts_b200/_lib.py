@@ -54,6 +54,7 @@ SIGNATURES = {
     "mtts_debug_set_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mtts_debug_set_tail_timeline": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtts_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "mtts_debug_set_tile_timeline": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtts_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "mtts_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),

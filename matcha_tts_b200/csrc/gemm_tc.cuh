@@ -121,6 +121,8 @@ struct GemmParams {
   int n_valid;
   // debug: per-CTA timeline [gridDim.x][16] (clock64 / globaltimer stamps), null in production
   long long* tl;
+  long long* tl2;  // debug: per-CTA per-tile stamps [gridDim.x][64]: tile i -> [4i] first operands seen by the MMA warp, [4i+1] last MMA
+                   // issued, [4i+2] accumulator seen by the epilogue, [4i+3] epilogue done (clock64; tools/gemm_tiles.py)
   int w_hint;  // 1: weight (B) tiles are loaded with the L2 evict_last policy
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
   int dbg;         // debug experiments (tools/gemm_repeat.py): 1 skip global stores, 2 skip smem staging + stores, 4 skip TMEM loads
@@ -405,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (dual_split && kc == rc0) { mbar_wait(&tempty_bar[1], aphase ^ 1); tc_fence_after(); }
         mbar_wait(&full_bar[stage], phase);
         if (tl && lane == 0 && kc == 0 && ti == 0) tl[3] = clock64();
+        if (p.tl2 && lane == 0 && kc == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
         const uint64_t da = umma_desc_sw128(sa);
@@ -432,6 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (tl && lane == 0) tl[4] = clock64();
+      if (p.tl2 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 1] = clock64();
       if (!DUAL_DOUBLE && rc0 < total_chunks) { aphase ^= 1; }   // dual accumulator with 256-wide tiles: one TMEM stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
@@ -474,6 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
+        if (p.tl2 && ew == 0 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 2] = clock64();
 
         float gs[(EPI == EPI_STATS) ? 2 * NCH : 1];
         float lsum = 0.f, lsq = 0.f;
@@ -941,6 +946,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
 
       if (tl && ew == 0 && lane == 0) tl[6] = clock64();
+      if (p.tl2 && ew == 0 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 3] = clock64();
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();

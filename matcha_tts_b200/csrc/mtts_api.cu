@@ -233,6 +233,7 @@ struct MttsHandle {
   long long* tl_buf = nullptr;
   long long* tail_tl = nullptr;  // ff_tail_kernel timeline (last launch wins), [148][128] int64
   int tl_max = 0, tl_count = 0;
+  long long* tl2_buf = nullptr;  // per-tile stamps of the GEMM launches (last launch wins), [148][64] int64
 };
 
 static const char* kStageNames[6] = {"down_blocks.0", "down_blocks.1", "mid_blocks.0",
@@ -554,6 +555,7 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   if (epi_is_gn(EPI) && h->gn_cap > 0 && grid > h->gn_cap) grid = h->gn_cap;
   GemmParams pp = p;
   pp.tl = nullptr;
+  pp.tl2 = h->tl2_buf;
   pp.w_hint = h->w_hint ? 1 : 0;
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
   pp.pdl_late = h->pdl_late ? 1 : 0;
@@ -584,7 +586,7 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
         const int units = ((m_tiles + 1) / 2) * p.n_tiles;
         const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
         GemmParams pp = p;
-        pp.tl = nullptr; pp.m_major = 0;
+        pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
         pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
         CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
                                stream, a0.d2, a1.d2, wmap.d2h, pp));
@@ -1405,6 +1407,12 @@ int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind,
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->prof_events.clear(); h->prof_kind.clear(); h->prof_flops.clear();
   return n;
+}
+
+int mtts_debug_set_tile_timeline(MttsHandle* h, void* dev_buf) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  h->tl2_buf = static_cast<long long*>(dev_buf);
+  return 0;
 }
 
 int mtts_debug_set_timeline(MttsHandle* h, void* dev_buf, int max_launches) {
