@@ -361,6 +361,35 @@ def run_native(args):
                 "share_of_solve": {k: round(v["ms"] / sum(x["ms"] for x in kinds.values()), 4) for k, v in kinds.items()},
                 "ms_per_solve_by_kernel": {k: round(v["ms"], 4) for k, v in kinds.items()}}
 
+    # ---- the dominant kernel on its own: block2's k3 conv (256 -> 256 channels) over the rows the F in-flight solves hold,
+    #      launched back to back (PDL on, operands L2-warm), CUDA events around the train -> against the BURST peak ----
+    if roof is not None:
+        rows_k, reps_k = F * B * (T + 2), 50
+        A_k = torch.randn(rows_k, 256, device=dev).half()
+        W_k = (torch.randn(256, 768, device=dev) / 27.7).half()
+        b_k = torch.randn(256, device=dev)
+        o_k = torch.empty(rows_k, 256, dtype=torch.float16, device=dev)
+        sh_k = (C.c_int * 3)(-1, 0, 1)
+        with torch.cuda.stream(stream):
+            def conv_once():
+                _lib.check(eng.lib.mtts_debug_gemm(eng.h, A_k.data_ptr(), W_k.data_ptr(), b_k.data_ptr(), o_k.data_ptr(), rows_k, 256, 256,
+                                                   3, sh_k, stream.cuda_stream))
+            for _ in range(5):
+                conv_once()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps_k):
+                conv_once()
+            e1.record(stream)
+            e1.synchronize()
+        us_k = e0.elapsed_time(e1) * 1e3 / reps_k
+        tf_k = 2.0 * rows_k * 256 * 768 / us_k / 1e6
+        burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1620.4) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1620.4
+        roof["kernel_alone"] = {"kernel": "gemm_tc_kernel<256, EPI_PLAIN> as a k3 Conv1d 256->256", "rows": rows_k, "us_per_launch": us_k,
+                                "achieved": tf_k, "peak": burst, "unit": "TFLOP/s", "frac": tf_k / burst,
+                                "note": f"{reps_k} back-to-back launches over the {rows_k} rows of {F} in-flight solves; burst bf16 peak"}
+
     if rank == 0:
         flop_step = B * T * n * (GEMM_FLOP_PER_FRAME_STEP + ATTN_FLOP_PER_FRAME_STEP_PER_T * T)
         cpu = None
