@@ -16,8 +16,10 @@
 #include "../../include/mtts.h"
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
+#include "ff_tail_pair.cuh"
 #include "gemm_tc.cuh"
 #include "ln_qkv.cuh"
 
@@ -138,6 +140,7 @@ struct StageW {
   TMap m_c1, m_c2, m_qkv;
   CUtensorMap m_wo, m_ff1, m_ff2;
   CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 128, 2}: half (K = 128) of one 128-wide hidden chunk of the fused tail (ff_tail.cuh)
+  CUtensorMap m_wo_h, m_ff2_h, t_ff1_h;  // CTA-pair tail (ff_tail_pair.cuh): each CTA stages half of every weight piece (128-row / 64-unit boxes)
 };
 
 struct WsLayout {
@@ -200,8 +203,10 @@ struct MttsHandle {
   bool fused_lnqkv = false; // MTTS_LNQKV=1: ln_qkv_kernel instead of the GroupNorm-apply+LayerNorm1 launch followed by the QKV GEMM (measured slower)
   bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
+  bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_pair_kernel (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
+  bool attn_v3 = true;   // MTTS_ATTN_V2=1: second-generation attention kernel (one thread per query row); default: attention3 (two threads per row)
   bool attn_v2 = true;   // MTTS_ATTN_V1=1: first-generation attention kernel (128-key tiles, V transposed by the QKV epilogue)
   int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
   bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
@@ -370,6 +375,9 @@ static int build_weight_maps(MttsHandle* h) {
     if (make_map(&w.m_ff1, a + w.ff1, 4 * C, C, C, 256)) return MTTS_ECUDA;
     if (make_map(&w.m_ff2, a + w.ff2, C, 4 * C, 4 * C, 256)) return MTTS_ECUDA;
     if (make_map3(&w.t_ff1, a + w.ff1, 4 * C, 4, C, 128, 2)) return MTTS_ECUDA;
+    if (make_map(&w.m_wo_h, a + w.wo, C, 128, 128, 128)) return MTTS_ECUDA;
+    if (make_map(&w.m_ff2_h, a + w.ff2, C, 4 * C, 4 * C, 128)) return MTTS_ECUDA;
+    if (make_map3(&w.t_ff1_h, a + w.ff1, 4 * C, 4, C, 64, 2)) return MTTS_ECUDA;
   }
   if (make_tmap(&h->m_down0, a + h->w_down0, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
   if (make_tmap(&h->m_down1, a + h->w_down1, C, 3 * C, 3 * C, 256)) return MTTS_ECUDA;
@@ -749,7 +757,8 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       Attn2Params ap{};
       ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
       ap.v = H(w.v); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
-      CUDA_TRY(launch_k(h, attention2_kernel, grid, dim3(ATT2_THREADS), ATT2_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
+      if (h->attn_v3) CUDA_TRY(launch_k(h, attention3_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
+      else CUDA_TRY(launch_k(h, attention2_kernel, grid, dim3(ATT2_THREADS), ATT2_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
     } else {
       AttnParams ap{};
       ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
@@ -768,7 +777,14 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       tp.tl = h->tail_tl;
       const int tiles = (lc.rows + 127) / 128;
       const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-      CUDA_TRY(launch_k(h, ff_tail_kernel, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
+      if (h->tail_pairs) {
+        const int units = (tiles + 1) / 2;
+        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+        CUDA_TRY(launch_k_pair(h, ff_tail_pair_kernel, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
+                               sw.m_ff2_h, tp));
+      } else {
+        CUDA_TRY(launch_k(h, ff_tail_kernel, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
+      }
       launched(h);
     }
     return 0;
@@ -1031,6 +1047,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIRS")) h->cta_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_ATTN_V1")) h->attn_v2 = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_ATTN_V2")) h->attn_v3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
@@ -1039,6 +1056,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
+  if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');
   build_tables(h);
@@ -1063,7 +1081,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(ff_tail_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ln_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
   } else {
