@@ -135,7 +135,7 @@ def test_midpoint_and_graph_equivalence(lj):
 # edge cases of the reference's contract
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,T,lengths", [(1, 2, None), (2, 4, [4, 1]), (3, 6, [6, 6, 2]), (1, 30, None),
-                                         (5, 34, [34, 33, 2, 17, 1]), (2, 130, [130, 129]), (1, 258, None)])
+                                         (5, 34, [34, 33, 2, 17, 1]), (2, 130, [130, 129]), (1, 258, None), (1, 384, None)])
 def test_small_and_ragged_shapes(lj, B, T, lengths):
     dec, cfg, sd = lj
     mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=B * 100 + T)
