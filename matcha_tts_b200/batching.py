@@ -111,11 +111,115 @@ def pad_batch(mus: Sequence[torch.Tensor], bucket: Bucket, device=None):
 _PINNED: Dict[tuple, List[torch.Tensor]] = {}     # recycled pinned host buffers (cudaHostAlloc is slow and synchronising)
 
 
-def _pinned(shape: tuple) -> torch.Tensor:
-    free = _PINNED.get(shape)
+class MelDict(dict):
+    """{utterance index: (n_feats, T_i) mel} whose values are views into ONE pinned host arena (frames-major).
+    `release()` hands the arena back for the next call (the views must not be used afterwards); an un-released
+    arena is simply owned by this dict and freed with it."""
+    arena: Optional[torch.Tensor] = None
+
+    def release(self):
+        if self.arena is not None:
+            _PINNED.setdefault(("arena", self.arena.numel()), []).append(self.arena)
+            self.arena = None
+            self.clear()
+
+
+def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[int, torch.Tensor]:
+    """CUDA path of solve_sharded.  Host work per bucket is a handful of launches, whatever the batch size:
+      * the local utterances are concatenated ONCE into a frames table (n_feats, total + 1), last column zero;
+      * padding a bucket is one index_select with indices computed on the host for all buckets at once (numpy) and
+        uploaded in one non-blocking copy from pinned memory -- no per-utterance slice copies, no synchronising
+        torch.tensor(..., device=cuda); the mask comes from the same indices; speaker rows are slices of one stack;
+      * the solved mel is compacted to its valid frames on the GPU and lands in one pinned arena; the result dict
+        holds views into it (no per-utterance host copies)."""
+    import numpy as np
+    n_feats = int(mus[0].shape[0]) if len(mus) else 0
+    local_ids = [i for bid in mine for i in buckets[bid].indices]
+    out = MelDict()
+    if not local_ids:
+        return out
+    lens = np.asarray([lengths[i] for i in local_ids], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)])                # frame offset of every local utterance in the table
+    total = int(offs[-1])
+    cur = torch.cuda.current_stream(dev)
+    src_dev = mus[local_ids[0]].device                            # encoder outputs on the GPU already, or one H2D copy of the table
+    table = torch.cat([mus[i].to(torch.float32) for i in local_ids] + [torch.zeros(n_feats, 1, device=src_dev)], dim=1)
+    table = table.to(dev)                                         # (n_feats, total + 1)
+    s_all = None
+    if spks is not None:
+        s_all = torch.stack([spks[i] for i in local_ids]).to(device=dev, dtype=torch.float32)
+    plan, flat_plan = _index_plan(buckets, mine, lens, offs)
+    pos = int(flat_plan.size)
+    plan_h = _pinned_i64(pos)
+    plan_h[:pos].copy_(torch.from_numpy(flat_plan))
+    plan_d = plan_h[:pos].to(dev, non_blocking=True)
+    arena = _pinned_arena(total * n_feats).view(total, n_feats)
+    streams = [torch.cuda.Stream(dev) for _ in range(lanes)] if lanes > 1 else [cur]
+    done = []
+    for k, (bk, r0, i0, i1, i2, f0, nv) in enumerate(plan):
+        B, T = len(bk.indices), bk.t_max
+        ls = streams[k % lanes]
+        if ls is not cur:
+            ls.wait_stream(cur)
+        with torch.cuda.stream(ls):
+            idx = plan_d[i0:i1]
+            mu = table.index_select(1, idx).view(n_feats, B, T).permute(1, 0, 2).contiguous()
+            mask = (idx != total).to(torch.float32).view(B, 1, T)
+            s = s_all[r0:r0 + B] if s_all is not None else None
+            mel = solver(mu, mask, s, bk).detach()
+            comp = mel.to(torch.float32).permute(0, 2, 1).reshape(B * T, n_feats).index_select(0, plan_d[i1:i2])
+            arena[f0:f0 + nv].copy_(comp, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(ls)
+        done.append(ev)
+    for ev in done:
+        ev.synchronize()
+    _PINNED.setdefault(("i64", plan_h.numel()), []).append(plan_h)
+    for j, i in enumerate(local_ids):
+        out[i] = arena[int(offs[j]):int(offs[j + 1])].t()          # (n_feats, T_i) view
+    out.arena = arena
+    return out
+
+
+def _index_plan(buckets, mine, lens, offs):
+    """Host-side index plan for the local buckets `mine` (utterances numbered in bucket order; `lens` / `offs` are their
+    lengths and frame offsets in the table, offs[-1] = total = the table's zero column).  Returns
+    ([(bucket, first row, i0, i1, i2, first frame, valid frames)], flat int64 array) where flat[i0:i1] are the gather
+    indices of the padded batch (B * T_max table columns, row-major) and flat[i1:i2] the positions of its valid frames."""
+    import numpy as np
+    total = int(offs[-1])
+    plan, pieces = [], []
+    row0 = pos = 0
+    for bid in mine:
+        bk = buckets[bid]
+        B, T = len(bk.indices), bk.t_max
+        ar = np.arange(T, dtype=np.int64)[None, :]
+        ln, of = lens[row0:row0 + B, None], offs[row0:row0 + B, None]
+        valid = ar < ln
+        idx = np.where(valid, of + ar, total).ravel()
+        vpos = np.flatnonzero(valid.ravel())
+        plan.append((bk, row0, pos, pos + idx.size, pos + idx.size + vpos.size, int(offs[row0]), int(vpos.size)))
+        pieces += [idx, vpos]
+        pos += idx.size + vpos.size
+        row0 += B
+    flat = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.int64)
+    return plan, flat
+
+
+def _pinned_i64(n: int) -> torch.Tensor:
+    n = max(1, 1 << (int(n) - 1).bit_length())                       # power-of-two sizes recycle well
+    free = _PINNED.get(("i64", n))
     if free:
         return free.pop()
-    return torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    return torch.empty(n, dtype=torch.int64, pin_memory=True)
+
+
+def _pinned_arena(n: int) -> torch.Tensor:
+    free = _PINNED.get(("arena", n))
+    if free:
+        return free.pop()
+    return torch.empty(n, dtype=torch.float32, pin_memory=True)
+
 
 
 Solver = Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Bucket], torch.Tensor]
@@ -148,34 +252,8 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
             local[i] = out[row, :, :lengths[i]].clone()
 
     dev = torch.device(device) if device is not None else None
-    if lanes > 1 and dev is not None and dev.type == "cuda":
-        streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
-        cur = torch.cuda.current_stream(dev)
-        pending = []                                   # (bucket, pinned host mel, event, device mel kept alive)
-        for k, bid in enumerate(mine):
-            bk = buckets[bid]
-            ls = streams[k % lanes]
-            ls.wait_stream(cur)
-            with torch.cuda.stream(ls):
-                mu, mask = pad_batch(mus, bk, dev)
-                s = None
-                if spks is not None:
-                    s = torch.stack([spks[i] for i in bk.indices]).to(device=dev, dtype=torch.float32)
-                out = solver(mu, mask, s, bk).detach()
-                host = _pinned(tuple(out.shape))
-                host.copy_(out, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(ls)
-            pending.append((bk, host, ev, out))
-            while len(pending) > 2 * lanes:            # bound the queue: finish the oldest bucket
-                b0, h0, e0, _ = pending.pop(0)
-                e0.synchronize()
-                unpack(b0, h0)
-                _PINNED.setdefault(tuple(h0.shape), []).append(h0)
-        for b0, h0, e0, _ in pending:
-            e0.synchronize()
-            unpack(b0, h0)
-            _PINNED.setdefault(tuple(h0.shape), []).append(h0)
+    if dev is not None and dev.type == "cuda":
+        local = _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, max(1, lanes))
     else:
         for bid in mine:
             bk = buckets[bid]
@@ -187,6 +265,8 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
             unpack(bk, out.detach().to("cpu", torch.float32))
     if not (use_dist and gather and world > 1):
         return local
+    if isinstance(local, MelDict):                          # views of one arena: pickle each utterance on its own
+        local = {i: v.contiguous() for i, v in local.items()}
     parts: List[Optional[dict]] = [None] * world
     dist.all_gather_object(parts, local, group=group)      # the only collective: finished mels
     merged: Dict[int, torch.Tensor] = {}

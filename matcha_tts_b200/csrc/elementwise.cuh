@@ -98,9 +98,8 @@ struct GnParams {
 };
 
 constexpr int GN_THREADS = 128;       // 4 warps
-constexpr int GN_ROWS_PER_BLOCK = 16; // 4 rows per warp, all in flight at once
-
-template <int MODE>
+// RPW rows per warp, all in flight at once (4 warps: 4 * RPW rows per block)
+template <int MODE, int RPW = 4>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) {
   pdl_launch_dependents();
   const int b = blockIdx.y;
@@ -123,11 +122,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   pdl_wait();
   // 1) issue every global load of this block up front (rows, time embedding, statistics partials):
   //    one memory round trip instead of three dependent ones
-  const int tw0 = blockIdx.x * GN_ROWS_PER_BLOCK + warp * 4;
-  uint4 yv[4], rv[4];
-  float m[4];
+  const int tw0 = (blockIdx.x * 4 + warp) * RPW;
+  uint4 yv[RPW], rv[RPW];
+  float m[RPW];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RPW; ++i) {
     const int t = tw0 + i;
     const size_t row = (size_t)b * p.Lp + t;
     yv[i] = make_uint4(0, 0, 0, 0);
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   }
   // 3) normalise, Mish, mask (+temb | +res, LayerNorm), store
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RPW; ++i) {
     const int t = tw0 + i;
     if (t >= p.Lp) continue;   // warp-uniform
     const size_t row = (size_t)b * p.Lp + t;

@@ -203,6 +203,7 @@ struct MttsHandle {
   bool fused_lnqkv = false; // MTTS_LNQKV=1: ln_qkv_kernel instead of the GroupNorm-apply+LayerNorm1 launch followed by the QKV GEMM (measured slower)
   bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
+  int gn_rpw = 4;           // MTTS_GN_RPW=8: GroupNorm-apply with 8 rows per warp in flight (32 rows per block) instead of 4
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_pair_kernel (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
@@ -691,14 +692,15 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     else if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
     else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
   }
-  const dim3 gn_grid((lc.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
+  const int gn_rows = 4 * h->gn_rpw;
+  const dim3 gn_grid((lc.Lp + gn_rows - 1) / gn_rows, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
   if (!fuse_gn) {
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
@@ -740,7 +742,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
       g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
       g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<1, 8> : gn_apply_kernel<1, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     }
     // q | k | v^T
     {
@@ -894,8 +896,9 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
-    const dim3 gn_grid((lT.Lp + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, w.B);
-    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    const int gn_rows = 4 * h->gn_rpw;
+    const dim3 gn_grid((lT.Lp + gn_rows - 1) / gn_rows, w.B);
+    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -1056,6 +1059,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
+  if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : 4;
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');

@@ -110,3 +110,38 @@ def test_two_rank_gloo_matches_single_process():
     for i in single:
         assert multi[i].shape == (80, lengths[i])
         assert torch.equal(multi[i], single[i])          # sharding must not change any utterance's result
+
+
+def test_index_plan_reproduces_padding_and_compaction():
+    """The CUDA path of solve_sharded pads with one gather and compacts with another (indices from _index_plan):
+    on CPU tensors the same indices must reproduce pad_batch exactly and invert it on the valid frames."""
+    import numpy as np
+    g = torch.Generator().manual_seed(9)
+    lengths = [int(x) for x in torch.randint(1, 90, (37,), generator=g)]
+    mus = [torch.randn(5, n, generator=g) for n in lengths]
+    buckets = Bt.make_buckets(lengths, max_frames=4 * 88, max_batch=6)
+    for world in (1, 3):
+        for mine in Bt.assign_buckets(buckets, world):
+            local_ids = [i for bid in mine for i in buckets[bid].indices]
+            if not local_ids:
+                continue
+            lens = np.asarray([lengths[i] for i in local_ids], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(lens)])
+            total = int(offs[-1])
+            table = torch.cat([mus[i] for i in local_ids] + [torch.zeros(5, 1)], dim=1)
+            plan, flat = Bt._index_plan(buckets, mine, lens, offs)
+            flat = torch.from_numpy(flat)
+            arena = torch.full((total, 5), float("nan"))
+            for bk, r0, i0, i1, i2, f0, nv in plan:
+                B, T = len(bk.indices), bk.t_max
+                idx = flat[i0:i1]
+                mu = table.index_select(1, idx).view(5, B, T).permute(1, 0, 2).contiguous()
+                mask = (idx != total).float().view(B, 1, T)
+                mu_ref, mask_ref = Bt.pad_batch(mus, bk)
+                assert torch.equal(mu, mu_ref) and torch.equal(mask, mask_ref)
+                assert local_ids[r0:r0 + B] == list(bk.indices)
+                comp = mu.permute(0, 2, 1).reshape(B * T, 5).index_select(0, flat[i1:i2])
+                assert comp.shape[0] == nv
+                arena[f0:f0 + nv] = comp
+            for j, i in enumerate(local_ids):
+                assert torch.equal(arena[int(offs[j]):int(offs[j + 1])].t(), mus[i])

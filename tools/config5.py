@@ -46,14 +46,21 @@ def main():
         torch.cuda.synchronize()
         return time.perf_counter() - t0, out
 
-    run()                                   # warm-up: captures one CUDA graph per (lane, bucket shape)
+    _, warm = run()                         # warm-up: captures one CUDA graph per (lane, bucket shape)
+    warm.release()                          # steady-state serving: the pinned result arena is handed back
     if world > 1:
         torch.distributed.barrier()
-    dt, out = run()
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dt = float(t.item())
+    dts = []
+    for rep in range(3):                    # three timed passes over the whole job; the median is reported
+        dt, out = run()
+        finite = bool(all(torch.isfinite(v).all() for v in out.values()))
+        out.release()
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)     # slowest rank
+            torch.distributed.barrier()
+        dts.append(float(t.item()))
+    dt = sorted(dts)[1]
     if rank == 0:
         valid = sum(lengths)
         padded = sum(b.padded_frames for b in buckets)
@@ -62,7 +69,7 @@ def main():
                                     (n_utt, sorted(lengths)[n_utt // 2]),
                           "n_gpus": world, "buckets": len(buckets), "buckets_rank0": len(mine), "seconds": dt,
                           "valid_frames_per_s": valid / dt, "padded_frames_per_s": padded / dt,
-                          "padding_overhead": padded / valid - 1.0, "finite": bool(all(torch.isfinite(v).all() for v in out.values()))}))
+                          "padding_overhead": padded / valid - 1.0, "finite": finite, "seconds_all_passes": dts}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
