@@ -154,7 +154,7 @@ def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[i
     plan_h[:pos].copy_(torch.from_numpy(flat_plan))
     plan_d = plan_h[:pos].to(dev, non_blocking=True)
     arena = _pinned_arena(total * n_feats).view(total, n_feats)
-    streams = [torch.cuda.Stream(dev) for _ in range(lanes)] if lanes > 1 else [cur]
+    streams = _lane_streams(dev, lanes) if lanes > 1 else [cur]
     done = []
     for k, (bk, r0, i0, i1, i2, f0, nv) in enumerate(plan):
         B, T = len(bk.indices), bk.t_max
@@ -179,6 +179,18 @@ def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[i
         out[i] = arena[int(offs[j]):int(offs[j + 1])].t()          # (n_feats, T_i) view
     out.arena = arena
     return out
+
+
+_LANES: Dict[tuple, list] = {}
+
+
+def _lane_streams(dev: torch.device, lanes: int) -> list:
+    """The lane streams of a device are created once: the decoder keeps one native engine (packed weights, workspaces,
+    captured graphs) per stream, so fresh streams on every call would rebuild all of that on every call."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), lanes)
+    if key not in _LANES:
+        _LANES[key] = [torch.cuda.Stream(dev) for _ in range(lanes)]
+    return _LANES[key]
 
 
 def _index_plan(buckets, mine, lens, offs):
