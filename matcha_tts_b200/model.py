@@ -55,6 +55,21 @@ def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     return path * mask
 
 
+def expand_by_duration(mu: torch.Tensor, duration: torch.Tensor, x_mask: torch.Tensor, y_mask: torch.Tensor) -> torch.Tensor:
+    """mu_y = path^T . mu of reference model.py:1284-1288 as a gather: with a hard monotonic path (one token per
+    frame) the dense (B, T_y, T_x) x (B, T_x, n_feats) product only copies column token(j) of mu to frame j, so the
+    result is bit-identical.  mu: (B, n_feats, T_x); duration: (B, T_x) integer-valued frames per token;
+    x_mask: (B, 1, T_x); y_mask: (B, 1, T_y) -> (B, n_feats, T_y).  Frames that no unmasked token covers are zero."""
+    t_y = y_mask.shape[-1]
+    ends = torch.cumsum(duration, 1)                                      # exclusive end frame of token i
+    frames = torch.arange(t_y, device=mu.device, dtype=ends.dtype)[None, :].expand(mu.shape[0], t_y).contiguous()
+    tok = torch.searchsorted(ends.contiguous(), frames, right=True)      # first token whose end lies beyond frame j
+    covered = tok < duration.shape[1]
+    tok = tok.clamp_max(duration.shape[1] - 1)
+    keep = (covered & (torch.gather(x_mask[:, 0] != 0, 1, tok)) & (y_mask[:, 0] != 0)).to(mu.dtype)
+    return torch.gather(mu, 2, tok[:, None, :].expand(-1, mu.shape[1], -1)) * keep[:, None, :]
+
+
 def denormalize(data: torch.Tensor, mu, std) -> torch.Tensor:
     """mel = data * std + mu (reference model.py:108-125); mu/std scalars or per-channel."""
     def prep(v):
@@ -467,7 +482,7 @@ class MatchaTTS(nn.Module):
         y_mask = sequence_mask(y_lengths, y_max_length_).unsqueeze(1).to(x_mask.dtype)
         attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
         attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
-        mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu.transpose(1, 2)).transpose(1, 2)
+        mu_y = expand_by_duration(mu, w_ceil.squeeze(1), x_mask, y_mask)   # == attn^T . mu (model.py:1288), as a gather
         mel = self.decoder(mu_y, y_mask, n_timesteps, temperature, spks, cond=None)
         mel = denormalize(mel, self.mel_mean, self.mel_std)
         return mel[:, :, :y_max_length], y_lengths, attn

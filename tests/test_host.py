@@ -127,6 +127,29 @@ def test_host_helpers():
     assert torch.allclose(denormalize(x, torch.tensor(1.0), torch.tensor(3.0)), torch.full((1, 2, 3), 4.0))
 
 
+def test_expand_by_duration_equals_dense_alignment_product():
+    """synthesize expands mu by a gather; the reference multiplies by the dense 0/1 path (model.py:1284-1288):
+    bit-identical, including zero-duration tokens, masked tokens, padded frames and an all-zero-duration row."""
+    from matcha_tts_b200 import generate_path, sequence_mask
+    from matcha_tts_b200.model import expand_by_duration, fix_len_compatibility
+    g = torch.Generator().manual_seed(3)
+    for trial in range(6):
+        b, tx, nf = 4, 9, 5
+        x_len = torch.tensor([9, 6, 1, 4])
+        x_mask = sequence_mask(x_len, tx).unsqueeze(1).float()
+        w_ceil = torch.randint(0, 5, (b, 1, tx), generator=g).float() * x_mask
+        if trial == 0:
+            w_ceil[2] = 0.0                                           # y_length clamps to 1, no token covers frame 0
+        mu = torch.randn(b, nf, tx, generator=g)
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        t_y = fix_len_compatibility(int(y_lengths.max()))
+        y_mask = sequence_mask(y_lengths, t_y).unsqueeze(1).float()
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1))
+        dense = torch.matmul(attn.transpose(1, 2), mu.transpose(1, 2)).transpose(1, 2)
+        assert torch.equal(expand_by_duration(mu, w_ceil.squeeze(1), x_mask, y_mask), dense)
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
 def test_host_helpers_equal_reference():
     from matcha_tts_b200 import fix_len_compatibility, generate_path, sequence_mask
