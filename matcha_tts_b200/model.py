@@ -67,7 +67,10 @@ def expand_by_duration(mu: torch.Tensor, duration: torch.Tensor, x_mask: torch.T
     covered = tok < duration.shape[1]
     tok = tok.clamp_max(duration.shape[1] - 1)
     keep = (covered & (torch.gather(x_mask[:, 0] != 0, 1, tok)) & (y_mask[:, 0] != 0)).to(mu.dtype)
-    return torch.gather(mu, 2, tok[:, None, :].expand(-1, mu.shape[1], -1)) * keep[:, None, :]
+    # like the reference's result -- a transposed view of a (B, T_y, n_feats) product (model.py:1288-1289) -- so that
+    # randn_like(mu_y) in the sampler (model.py:1085) lays the noise out in the same memory order for the same seed
+    out = torch.gather(mu.transpose(1, 2), 1, tok[:, :, None].expand(-1, -1, mu.shape[1])) * keep[:, :, None]
+    return out.transpose(1, 2)
 
 
 def denormalize(data: torch.Tensor, mu, std) -> torch.Tensor:

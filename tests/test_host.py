@@ -147,7 +147,8 @@ def test_expand_by_duration_equals_dense_alignment_product():
         attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
         attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1))
         dense = torch.matmul(attn.transpose(1, 2), mu.transpose(1, 2)).transpose(1, 2)
-        assert torch.equal(expand_by_duration(mu, w_ceil.squeeze(1), x_mask, y_mask), dense)
+        got = expand_by_duration(mu, w_ceil.squeeze(1), x_mask, y_mask)
+        assert torch.equal(got, dense) and got.stride() == dense.stride()    # same memory order: randn_like(mu_y) draws alike
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
