@@ -700,7 +700,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : h->gn_rpw == 2 ? gn_apply_kernel<0, 2> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
@@ -742,7 +742,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
       g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
       g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<1, 8> : gn_apply_kernel<1, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<1, 8> : h->gn_rpw == 2 ? gn_apply_kernel<1, 2> : gn_apply_kernel<1, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     }
     // q | k | v^T
     {
@@ -898,7 +898,7 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
     const int gn_rows = 4 * h->gn_rpw;
     const dim3 gn_grid((lT.Lp + gn_rows - 1) / gn_rows, w.B);
-    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : h->gn_rpw == 2 ? gn_apply_kernel<0, 2> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -1059,7 +1059,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
-  if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : 4;
+  if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : atoi(e) == 2 ? 2 : 4;
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');

@@ -97,6 +97,82 @@ def test_against_reference_golden(case, golden, lj, vctk):
 
 
 # ---------------------------------------------------------------------------------------------
+# every intermediate of ONE estimator evaluation against the oracle trace (launch by launch)
+# ---------------------------------------------------------------------------------------------
+def test_estimator_stage_trace():
+    """Runs the estimator with a growing launch limit and compares each kernel's output buffer with the oracle's
+    named intermediates (reference model.py:773-790 Block1D / ResnetBlock1D, :670-705 attention, :733-744 transformer
+    block, :997-1043 level convs, :1045 final block): a wrong stage cannot hide behind the end-to-end tolerance."""
+    dec, cfg, sd = U.make_decoder(160)
+    dec.set_chains(1)                                   # one chain: the launch order is the stage order
+    eng = dec._engine(torch.device("cuda", 0))
+    B, T = 3, 48
+    H, LpT, LpH = T // 2, T + 2, T // 2 + 1
+    mu, mask, z0, spks = O.make_inputs(cfg, B, T, [48, 31, 16], seed=12)
+    t = torch.linspace(0.05, 0.9, B)
+    trace = {}
+    ref = O.estimator_forward(sd, cfg, z0, mask, mu, t, spks, emu=O.Emu(trace=trace))
+    worst = {}
+
+    def run(limit):
+        _check = eng.lib.mtts_debug_set_launch_limit(eng.h, limit)
+        assert _check == 0
+        out = dec(_d(z0), _d(mask), _d(mu), _d(t))
+        torch.cuda.synchronize()
+        return out
+
+    def cmp(name, got, want, tol=5e-3):
+        ma, rl = U.errs(got, want)
+        worst[name] = max(worst.get(name, 0.0), rl)
+        assert rl < tol, (name, ma, rl)
+
+    def buf(name, L, Lp, cols):
+        return U.flat_to_bct(U.ws_tensor(eng, B, T, name, B * Lp, cols), B, L, Lp)
+
+    try:
+        run(6)                                           # prologue: masks, row maps, operand staging, time table
+        cmp("x0", buf("x0", T, LpT, 256)[:, :160], torch.cat([z0, mu], 1) * mask)
+        te6 = U.ws_tensor(eng, B, T, "te6", B, 1536, torch.float32)
+        for s_, (nm, _) in enumerate(O.stage_names(cfg)):
+            tau = torch.nn.functional.linear(torch.nn.functional.mish(trace["temb"]), sd[nm + ".0.mlp.1.weight"],
+                                             sd[nm + ".0.mlp.1.bias"])
+            cmp(f"te6[{s_}]", te6[:, s_ * 256:(s_ + 1) * 256], tau, 1e-4)
+        stages = [("down_blocks.0", T, LpT, "skip0"), ("down_blocks.1", H, LpH, "skip1"), ("mid_blocks.0", H, LpH, "xM0"),
+                  ("mid_blocks.1", H, LpH, "xM1"), ("up_blocks.0", H, LpH, "xU0s"), ("up_blocks.1", T, LpT, "xU1s")]
+        lvl_after = {0: ("xD0", H, LpH), 1: ("xD1", H, LpH), 4: ("xU0", T, LpT), 5: ("xF", T, LpT)}
+        base = 6
+        for si, (nm, L, Lp, outname) in enumerate(stages):
+            pf = nm + ":"
+            run(base + 1)                                # block1 conv + res_conv (second accumulator)
+            cmp(pf + "y1", buf("y", L, Lp, 256), trace[pf + "y.block1"])
+            cmp(pf + "res", buf("res", L, Lp, 256), trace[pf + "res"])
+            run(base + 2); cmp(pf + "h1", buf("h1", L, Lp, 256), trace[pf + "h1"])           # GN-apply + Mish + temb
+            run(base + 3); cmp(pf + "y2", buf("y", L, Lp, 256), trace[pf + "y.block2"])      # block2 conv
+            run(base + 4)                                # GN-apply + Mish + residual, LayerNorm1
+            cmp(pf + "xr", buf("xr", L, Lp, 256), trace[pf + "xr"])
+            cmp(pf + "a", buf("a", L, Lp, 256), trace[pf + "a"].transpose(1, 2))
+            run(base + 5)                                # q | k | v (q pre-scaled by head_dim^-1/2)
+            cmp(pf + "q", buf("q", L, Lp, 128), trace[pf + "q"].transpose(1, 2) * 0.125)
+            cmp(pf + "k", buf("k", L, Lp, 128), trace[pf + "k"].transpose(1, 2))
+            cmp(pf + "v", buf("v", L, Lp, 128), trace[pf + "v"].transpose(1, 2))
+            run(base + 6); cmp(pf + "o", buf("o", L, Lp, 128), trace[pf + "o"].transpose(1, 2))   # attention (quirk rows too)
+            run(base + 7); cmp(pf + "out", buf(outname, L, Lp, 256), trace[pf + "out"])      # fused transformer tail
+            base += 7
+            if si in lvl_after:
+                nm2, L2, Lp2 = lvl_after[si]
+                run(base + 1); cmp(nm2, buf(nm2, L2, Lp2, 256), trace[nm2])                   # down / up / level conv
+                base += 1
+        run(base + 2); cmp("hF", buf("h1", T, LpT, 256), trace["hF"])                        # final block
+        out = run(-1)
+        assert dec.last_launch_count() == base + 3               # 6 prologue + 49 per evaluation
+        ma, rl = O.parity_errors(out.cpu(), ref, mask)
+        assert ma <= O.TOL_MAX_ABS and rl <= EST_REL, (ma, rl)
+    finally:
+        eng.lib.mtts_debug_set_launch_limit(eng.h, -1)
+    print("worst relative errors per intermediate:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+
+
+# ---------------------------------------------------------------------------------------------
 # BASELINE.json configs at reduced batch, 10 Euler steps, against the oracle
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cin,B,T,lengths,n,seed", [
