@@ -26,6 +26,15 @@
 // groups per TMEM lane quarter).  The MMA stream is software-pipelined over the 8 hidden chunks
 //   FF1_0 | FF1_1 FF2_0 | FF1_2 FF2_1 | ... | FF1_7 FF2_6 | FF2_7
 // so that the tensor pipe works on FF1_{j+1} and FF2_{j-1} while the epilogue warps apply SnakeBeta to chunk j.
+//
+// CG = 2 is the CTA-pair variant (same maths, same TMEM / shared-memory plan per CTA): a cluster of two CTAs works on two
+// consecutive 128-row tiles with tcgen05 cta_group::2 MMAs (M = 256).  Each CTA stages only ITS HALF of every weight
+// piece (Wo / W2: 128 of the 256 output rows, W1: 64 of the chunk's 128 hidden units; the tensor maps have half-size
+// boxes), so the shared-memory traffic of the FF loop -- the bound of the single-CTA kernel --
+// drops from ~320 KB to ~192 KB per hidden chunk.  The pair leader (cluster rank 0) issues every MMA; its ring "full"
+// barriers count the bytes of both CTAs' TMA loads (the peer's loads complete_tx on the leader's barrier), ring "empty"
+// and every MMA -> epilogue barrier is signalled in both CTAs by multicast commits, and every epilogue -> MMA barrier
+// lives in the leader and collects the epilogue warps of both CTAs (the peer arrives through its shared::cluster address).
 #pragma once
 #include <cuda.h>
 
@@ -70,9 +79,15 @@ constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;
 constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;
 static_assert(TAIL_SMEM <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
 
+template <int CG>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmWo,
                const __grid_constant__ CUtensorMap tmW1_3, const __grid_constant__ CUtensorMap tmW2, const TailParams p) {
+  static_assert(CG == 1 || CG == 2, "one CTA per row tile, or a CTA pair per two row tiles");
+  // CG == 2: tmWo / tmW2 have 128-row boxes (this CTA's half of the 256 output rows), tmW1_3 box {64, 64 hidden units, 2 K-chunks}
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
+  // a unit = CG consecutive row tiles, one per CTA of the pair
+  const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int NCG = TAIL_NCG;
   constexpr int NEW = 4 * NCG;       // epilogue warps
   constexpr int CW1 = 256 / NCG;     // columns per warp in the 256-wide phases
@@ -100,17 +115,21 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!p.pdl_late) pdl_launch_dependents();   // late: when the CTA's last tile reaches its final epilogue (see gemm_tc.cuh)
   const int m_tiles = (p.M + 127) / 128;
+  const int m_units = (m_tiles + CG - 1) / CG;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAIL_NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(r_full, 1); mbar_init(c_ready, NEW);
-    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NEW); }
-    for (int i = 0; i < TAIL_NSB; ++i) { mbar_init(&s_ready[i], NEW); mbar_init(&s_empty[i], 1); }
-    mbar_init(r_done, 1); mbar_init(r_empty, NEW);
+    mbar_init(r_full, 1); mbar_init(c_ready, CG * NEW);
+    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], CG * NEW); }
+    for (int i = 0; i < TAIL_NSB; ++i) { mbar_init(&s_ready[i], CG * NEW); mbar_init(&s_empty[i], 1); }
+    mbar_init(r_done, 1); mbar_init(r_empty, CG * NEW);
     fence_mbar_init();
     tma_prefetch_desc(&tmO3); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1_3); tma_prefetch_desc(&tmW2);
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   if (warp >= 3) {  // weights-only parameters: staged while the previous kernel drains
     for (int i = threadIdx.x - 96; i < 256; i += 32 * NEW) {
       s_par[i] = p.b_o[i]; s_par[256 + i] = p.ln_g[i]; s_par[512 + i] = p.ln_b[i]; s_par[768 + i] = p.b2[i];
@@ -120,7 +139,8 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tR = tmem_base;
@@ -130,64 +150,92 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     // converged warp, one elected lane per instruction (keeps descriptors/coordinates in uniform registers)
-    if ((int)blockIdx.x < m_tiles) {
+    if (unit0 < m_units) {
       uint32_t it = 0;  // running ring item counter
       const uint64_t pol = l2_policy_evict_last();
+      constexpr uint32_t WBYTES = TAIL_PIECE / CG;   // this CTA's share of a weight piece
       auto slot_acquire = [&]() -> uint32_t {
         const uint32_t slot = it % TAIL_NST, use = it / TAIL_NST;
         mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
         ++it;
         return slot;
       };
-      auto put2 = [&](const CUtensorMap* tm, int c0, int c1) {  // weights: [256 rows x 64 cols]
+      // CG == 2: every load signals the LEADER's full barrier; the leader's producer arrives once per item and expects the
+      // bytes of both CTAs (the peer's complete_tx may come first: the transaction count runs negative inside the phase)
+      auto put2 = [&](const CUtensorMap* tm, int c0) {  // weights: this CTA's 256 / CG output rows x 64 cols
         const uint32_t slot = slot_acquire();
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
-          if (p.w_hint) tma_load_2d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, tm, &full_bar[slot], c0, c1, pol);
-          else tma_load_2d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, tm, &full_bar[slot], c0, c1);
+          uint8_t* dst = smem + TAIL_OFF_RING + slot * TAIL_PIECE;
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * WBYTES);
+          if constexpr (CG == 2) {
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[slot]), 0);
+            if (p.w_hint) tma_load_2d_pair_hint(dst, tm, lbar, c0, (int)crank * 128, pol);
+            else tma_load_2d_pair(dst, tm, lbar, c0, (int)crank * 128);
+          } else {
+            if (p.w_hint) tma_load_2d_hint(dst, tm, &full_bar[slot], c0, 0, pol);
+            else tma_load_2d(dst, tm, &full_bar[slot], c0, 0);
+          }
         }
         __syncwarp();
       };
-      auto put_w1 = [&](int j) {   // hidden units [128j, 128j+128): two pieces of K = 128 each
+      auto put_w1 = [&](int j) {   // hidden units [128j + (128 / CG) rank, + 128 / CG): two pieces of K = 128 each
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t slot = slot_acquire();
           if (elect_one()) {
-            mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
-            if (p.w_hint) tma_load_3d_hint(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh, pol);
-            else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh);
+            uint8_t* dst = smem + TAIL_OFF_RING + slot * TAIL_PIECE;
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * WBYTES);
+            if constexpr (CG == 2) {
+              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[slot]), 0);
+              if (p.w_hint) tma_load_3d_pair_hint(dst, &tmW1_3, lbar, 0, j * 128 + (int)crank * 64, 2 * hh, pol);
+              else tma_load_3d_pair(dst, &tmW1_3, lbar, 0, j * 128 + (int)crank * 64, 2 * hh);
+            } else {
+              if (p.w_hint) tma_load_3d_hint(dst, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh, pol);
+              else tma_load_3d(dst, &tmW1_3, &full_bar[slot], 0, j * 128, 2 * hh);
+            }
           }
           __syncwarp();
         }
       };
       bool first = true;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-        put2(&tmWo, 0, 0);   // Wo K-chunk 0
-        put2(&tmWo, 64, 0);  // Wo K-chunk 1
+      for (int unit = unit0; unit < m_units; unit += nunits) {
+        const int tile = CG * unit + (int)crank;   // CG == 2: may be == m_tiles on the last unit (rows out of range load as zeros)
+        put2(&tmWo, 0);    // Wo K-chunk 0
+        put2(&tmWo, 64);   // Wo K-chunk 1
         if (first) { pdl_wait(); first = false; }  // o is the first operand produced by the previous kernel
         {
           const uint32_t slot = slot_acquire();
           if (elect_one()) {
-            mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
-            tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, &full_bar[slot], 0, tile * 128, 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * TAIL_PIECE);   // each CTA loads its own row tile of o
+            if constexpr (CG == 2) tma_load_3d_pair(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, mapa_u32(smem_u32(&full_bar[slot]), 0), 0, tile * 128, 0);
+            else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, &full_bar[slot], 0, tile * 128, 0);
           }
           __syncwarp();
         }
         put_w1(0);
         put_w1(1);
         for (int j = 0; j < TAIL_NJ; ++j) {   // tensor-pipe order: FF1_{j+1} FF2_j FF1_{j+2} FF2_{j+1} ...
-          put2(&tmW2, j * 128, 0);
-          put2(&tmW2, j * 128 + 64, 0);
+          put2(&tmW2, j * 128);
+          put2(&tmW2, j * 128 + 64);
           if (j + 2 < TAIL_NJ) put_w1(j + 2);
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================================== MMA issuers ======================================
+  } else if ((warp == 1 || warp == 2) && crank == 0) {
+    // ===================================== MMA issuers (CG == 2: pair leader only) ============
     // Converged warps (addresses and descriptors stay in uniform registers); only the tcgen05 instructions are
     // issued by one elected lane.  Warp 1 owns the to_out + FF1 stream (accumulators R then D1), warp 2 the FF2
     // stream (accumulates into R); both walk the same ring-item numbering as the producer.
-    constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
-    constexpr uint32_t idesc128 = umma_idesc_f16(128, 128);
+    constexpr uint32_t idesc256 = umma_idesc_f16(128 * CG, 256);   // CG == 2: M = 256, both CTAs' 128 rows
+    constexpr uint32_t idesc128 = umma_idesc_f16(128 * CG, 128);
+    auto mma_ss = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+      if constexpr (CG == 2) umma_f16_pair(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+    };
+    auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+      if constexpr (CG == 2) umma_f16_ts_pair(d, a, b, idesc, acc); else umma_f16_ts(d, a, b, idesc, acc);
+    };
+    auto commit = [](uint64_t* bar) {   // CG == 2: arrives on the barrier at this offset in BOTH CTAs
+      if constexpr (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
+    };
     const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
     const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
     auto slot_wait = [&](uint32_t item) -> uint32_t {
@@ -201,11 +249,11 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     auto item_w1 = [](int k) -> uint32_t { return k < 2 ? 3u + 2u * k : 4u * k + 1u; };          // first of two
     auto item_w2 = [](int j) -> uint32_t { return j <= 5 ? 7u + 4u * j : 31u + 2u * (j - 6); };  // first of two
     constexpr uint32_t ITEMS = 35;
-    long long* tl = (p.tl != nullptr) ? p.tl + (size_t)blockIdx.x * 128 : nullptr;
+    long long* tl = (p.tl != nullptr) ? p.tl + (size_t)unit0 * 128 : nullptr;
     uint32_t n_tile = 0;
     if (warp == 1) {
       uint32_t n_d1e = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+      for (int unit = unit0; unit < m_units; unit += nunits, ++n_tile) {
         if (n_tile != 0) tl = nullptr;
         const uint32_t base = n_tile * ITEMS;
         // ---- to_out: R = o Wo^T
@@ -219,9 +267,9 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
             const uint64_t da = umma_desc_sw128(a + k * 16384), db = umma_desc_sw128(b);
             if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, (k | kk) != 0);
-              umma_commit(&empty_bar[(base + k) % TAIL_NST]);
-              if (k == 1) { umma_commit(&empty_bar[(base + 2) % TAIL_NST]); umma_commit(r_full); }
+              for (int kk = 0; kk < 4; ++kk) mma_ss(tR, da + 2 * kk, db + 2 * kk, idesc256, (k | kk) != 0);
+              commit(&empty_bar[(base + k) % TAIL_NST]);
+              if (k == 1) { commit(&empty_bar[(base + 2) % TAIL_NST]); commit(r_full); }
             }
             __syncwarp();
           }
@@ -244,10 +292,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
 #pragma unroll
               for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B descriptor address in 16-byte units
-                  umma_f16_ts(tD1, tC + (2 * hh + sub) * 32 + kk * 8, db0 + sub * (16384 >> 4) + 2 * kk, idesc128, (hh | sub | kk) != 0);
-              umma_commit(&empty_bar[item % TAIL_NST]);
-              if (hh == 1) umma_commit(&d1_full[0]);
+                for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B: this CTA's 128 / CG hidden units x 64 per K-chunk (16 / CG KB)
+                  mma_ts(tD1, tC + (2 * hh + sub) * 32 + kk * 8, db0 + sub * ((16384 / CG) >> 4) + 2 * kk, idesc128, (hh | sub | kk) != 0);
+              commit(&empty_bar[item % TAIL_NST]);
+              if (hh == 1) commit(&d1_full[0]);
             }
             __syncwarp();
           }
@@ -256,7 +304,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       }
     } else {
       uint32_t n_sr = 0;   // FF2 chunks consumed so far (buffer = n % 3, use = n / 3)
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+      for (int unit = unit0; unit < m_units; unit += nunits, ++n_tile) {
         if (n_tile != 0) tl = nullptr;
         const uint32_t base = n_tile * ITEMS;
         mbar_wait(c_ready, n_tile & 1);   // x_a is in R
@@ -273,11 +321,11 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
             const uint64_t da = umma_desc_sw128(sbuf + b * TAIL_SBYTES + hh * 16384), db = umma_desc_sw128(w);
             if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
-              umma_commit(&empty_bar[item % TAIL_NST]);
+              for (int kk = 0; kk < 4; ++kk) mma_ss(tR, da + 2 * kk, db + 2 * kk, idesc256, 1u);  // on top of x_a
+              commit(&empty_bar[item % TAIL_NST]);
               if (hh == 1) {
-                umma_commit(&s_empty[b]);
-                if (j == TAIL_NJ - 1) umma_commit(r_done);
+                commit(&s_empty[b]);
+                if (j == TAIL_NJ - 1) commit(r_done);
               }
             }
             __syncwarp();
@@ -286,8 +334,12 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         }
       }
     }
-  } else {
+  } else if (warp >= 3) {
     // ===================================== epilogue =========================================
+    // CG == 2: the epilogue -> MMA barriers live in the pair leader: arrive through the shared::cluster address
+    auto arrive_leader = [&](uint64_t* bar) {
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0)); else mbar_arrive(bar);
+    };
     const int ew = warp - 3;
     const int q = warp & 3;     // TMEM lane quarter
     const int cg = ew >> 2;     // column group
@@ -298,10 +350,11 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const int trow = q * 32 + lane;  // row inside the tile
     uint32_t n_tile = 0, n_d1f[2] = {0, 0}, n_s = 0;   // n_s: s chunks produced so far (buffer = n % 3, use = n / 3)
-    long long* tl = (p.tl != nullptr && ew == 0 && lane == 0) ? p.tl + (size_t)blockIdx.x * 128 + 64 : nullptr;
+    long long* tl = (p.tl != nullptr && ew == 0 && lane == 0 && crank == 0) ? p.tl + (size_t)unit0 * 128 + 64 : nullptr;
     pdl_wait();  // x_r / out belong to the dependency chain
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++n_tile) {
+    for (int unit = unit0; unit < m_units; unit += nunits, ++n_tile) {
       if (n_tile != 0) tl = nullptr;
+      const int tile = CG * unit + (int)crank;
       const int rw0 = tile * 128 + q * 32;
       const int row = rw0 + lane;
       const int rows_valid = min(32, p.M - rw0);
@@ -368,7 +421,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(c_ready);
+        if (lane == 0) arrive_leader(c_ready);
         if (tl) tl[1] = clock64();
       }
       // ------------------------------------------------ E2: SnakeBeta on the 8 hidden chunks
@@ -389,7 +442,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&d1_empty[0]);  // the accumulator chunk is in registers: FF1_{j+1} may overwrite it
+        if (lane == 0) arrive_leader(&d1_empty[0]);  // the accumulator chunk is in registers: FF1_{j+1} may overwrite it
         const uint32_t pb = spar + (1024 + j * 128 + cg * 32) * 4;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -411,7 +464,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
                             pack_h2_sat(v[8 * u + 4], v[8 * u + 5]), pack_h2_sat(v[8 * u + 6], v[8 * u + 7])));
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_ready[sb]);
+        if (lane == 0) arrive_leader(&s_ready[sb]);
         if (tl && j < 8) tl[5 + 2 * j] = clock64();
       }
       // ------------------------------------------------ E3: out = (x_a + FF + b2) * mask
@@ -420,7 +473,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         if (row < p.M) mrow = p.rowmask[row];
         if (lane == 0) {
           mbar_wait(r_done, n_tile & 1);
-          if (p.pdl_late && tile + (int)gridDim.x >= m_tiles) pdl_launch_dependents();
+          if (p.pdl_late && unit + nunits >= m_units) pdl_launch_dependents();
         }
         __syncwarp();
         tc_fence_after();
@@ -437,7 +490,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           if (c == NCH1 - 1) {   // the whole accumulator is in registers: the next tile's to_out may overwrite R while this one is stored
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(r_empty);
+            if (lane == 0) arrive_leader(r_empty);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -455,8 +508,12 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (CG == 2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the last commit has completed
+  else __syncthreads();
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 }  // namespace mtts

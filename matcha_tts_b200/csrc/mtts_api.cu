@@ -19,7 +19,6 @@
 #include "attention3.cuh"
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
-#include "ff_tail_pair.cuh"
 #include "gemm_tc.cuh"
 #include "ln_qkv.cuh"
 
@@ -140,7 +139,7 @@ struct StageW {
   TMap m_c1, m_c2, m_qkv;
   CUtensorMap m_wo, m_ff1, m_ff2;
   CUtensorMap t_ff1;  // W1 as [4][1024][64], box {64, 128, 2}: half (K = 128) of one 128-wide hidden chunk of the fused tail (ff_tail.cuh)
-  CUtensorMap m_wo_h, m_ff2_h, t_ff1_h;  // CTA-pair tail (ff_tail_pair.cuh): each CTA stages half of every weight piece (128-row / 64-unit boxes)
+  CUtensorMap m_wo_h, m_ff2_h, t_ff1_h;  // CTA-pair tail (ff_tail_kernel<2>): each CTA stages half of every weight piece (128-row / 64-unit boxes)
 };
 
 struct WsLayout {
@@ -204,7 +203,7 @@ struct MttsHandle {
   bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   int gn_rpw = 4;           // MTTS_GN_RPW=8: GroupNorm-apply with 8 rows per warp in flight (32 rows per block) instead of 4
-  bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_pair_kernel (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
+  bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   bool attn_v3 = true;   // MTTS_ATTN_V2=1: second-generation attention kernel (one thread per query row); default: attention3 (two threads per row)
@@ -782,10 +781,10 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       if (h->tail_pairs) {
         const int units = (tiles + 1) / 2;
         const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
-        CUDA_TRY(launch_k_pair(h, ff_tail_pair_kernel, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
+        CUDA_TRY(launch_k_pair(h, ff_tail_kernel<2>, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
                                sw.m_ff2_h, tp));
       } else {
-        CUDA_TRY(launch_k(h, ff_tail_kernel, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
+        CUDA_TRY(launch_k(h, ff_tail_kernel<1>, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
       }
       launched(h);
     }
@@ -1086,8 +1085,8 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
-    if (cudaFuncSetAttribute(ff_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
-    if (cudaFuncSetAttribute(ff_tail_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(ff_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(ff_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ln_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
   } else {
