@@ -119,7 +119,7 @@ class MelDict(dict):
 
     def release(self):
         if self.arena is not None:
-            _PINNED.setdefault(("arena", self.arena.numel()), []).append(self.arena)
+            _release_arena(self.arena)
             self.arena = None
             self.clear()
 
@@ -226,12 +226,33 @@ def _pinned_i64(n: int) -> torch.Tensor:
     return torch.empty(n, dtype=torch.int64, pin_memory=True)
 
 
-def _pinned_arena(n: int) -> torch.Tensor:
-    free = _PINNED.get(("arena", n))
-    if free:
-        return free.pop()
-    return torch.empty(n, dtype=torch.float32, pin_memory=True)
+_ARENA_POOL_BYTES = 2 << 30     # released result arenas kept for reuse (pinned memory is a limited resource)
 
+
+def _pinned_arena(n: int) -> torch.Tensor:
+    """A pinned fp32 buffer of >= n elements: the smallest released arena that fits (and is not more than twice too
+    large), else a fresh one rounded up to 1 Mi elements so that similar-sized jobs recycle each other's arenas."""
+    best = None
+    for key, free in _PINNED.items():
+        if key[0] == "arena" and free and n <= key[1] <= 2 * max(n, 1 << 20) and (best is None or key[1] < best[1]):
+            best = key
+    if best is not None:
+        return _PINNED[best].pop()[:n]
+    return torch.empty(((n + (1 << 20) - 1) >> 20) << 20, dtype=torch.float32, pin_memory=True)[:n]
+
+
+def _release_arena(arena: torch.Tensor):
+    base = arena._base if arena._base is not None else arena      # the whole allocation, not the [:n] view
+    while base._base is not None:
+        base = base._base
+    _PINNED.setdefault(("arena", base.numel()), []).append(base)
+    pooled = [(k, t) for k, lst in _PINNED.items() if k[0] == "arena" for t in lst]
+    total = sum(k[1] * 4 for k, _ in pooled)
+    for k, t in pooled:                                            # oldest first
+        if total <= _ARENA_POOL_BYTES:
+            break
+        _PINNED[k] = [x for x in _PINNED[k] if x is not t]
+        total -= k[1] * 4
 
 
 Solver = Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Bucket], torch.Tensor]

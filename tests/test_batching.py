@@ -145,3 +145,33 @@ def test_index_plan_reproduces_padding_and_compaction():
                 arena[f0:f0 + nv] = comp
             for j, i in enumerate(local_ids):
                 assert torch.equal(arena[int(offs[j]):int(offs[j + 1])].t(), mus[i])
+
+
+def test_result_arena_pool_recycles_and_stays_bounded(monkeypatch):
+    """MelDict.release() hands the pinned result arena back; the pool reuses the smallest arena that fits, walks views
+    back to the whole allocation and never keeps more than _ARENA_POOL_BYTES (pinning stubbed out: no GPU here)."""
+    orig = torch.empty
+
+    def unpinned(*a, **k):
+        k.pop("pin_memory", None)
+        return orig(*a, **k)
+
+    monkeypatch.setattr(torch, "empty", unpinned)
+    monkeypatch.setattr(Bt, "_PINNED", {})
+    a = Bt._pinned_arena(3_000_000)
+    assert a.numel() == 3_000_000 and a._base.numel() == 3 << 20
+    d = Bt.MelDict({0: a.view(-1, 80)[:10].t()})
+    d.arena = a.view(-1, 80)
+    d.release()
+    assert len(d) == 0 and d.arena is None and len(Bt._PINNED[("arena", 3 << 20)]) == 1
+    d.release()                                                   # idempotent
+    b = Bt._pinned_arena(2_900_000)                               # similar size: recycled
+    assert b._base.numel() == 3 << 20 and not Bt._PINNED[("arena", 3 << 20)]
+    c = Bt._pinned_arena(100)                                     # much smaller: its own arena, not a slice of 12 MB
+    assert c._base.numel() == 1 << 20
+    Bt._release_arena(b)
+    Bt._release_arena(c)
+    assert Bt._pinned_arena(500_000)._base.numel() == 1 << 20
+    monkeypatch.setattr(Bt, "_ARENA_POOL_BYTES", 13 << 20)
+    Bt._release_arena(Bt._pinned_arena(900_000))                  # 12 MB + 4 MB pooled > 13 MB: the oldest goes
+    assert sum(k[1] * 4 * len(v) for k, v in Bt._PINNED.items() if k[0] == "arena") <= 13 << 20
