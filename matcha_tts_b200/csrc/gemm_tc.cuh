@@ -127,6 +127,9 @@ struct GemmParams {
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
   int dbg;         // debug experiments (tools/gemm_repeat.py): 1 skip global stores, 2 skip smem staging + stores, 4 skip TMEM loads
   int pdl_late;    // 1: griddepcontrol.launch_dependents when the CTA's last accumulator is complete instead of at entry
+  int tap3;        // 1 (256-wide single-CTA conv tiles only): the three segments are the -1 / 0 / +1 taps of ONE source with the
+                   //    same columns; tmA1 is that source with a 130-row box and one (128 + 2)-row activation tile per K chunk
+                   //    feeds all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu)
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -238,6 +241,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // tap-sharing mode (p.tap3): the ring region is re-cut into an activation ring of TAP_A_STAGES x 17 KB (130 rows x 128 B)
+  // and a weight ring of STAGES x 32 KB; full_bar / empty_bar guard the weight ring, afull / aempty the activation ring
+  constexpr bool TAP3_OK = (BN == 256 && KSUB == 1 && CG == 1 && (EPI == EPI_STATS || EPI == EPI_PLAIN));
+  constexpr int TAP_A_BYTES = 17 * 1024, TAP_A_STAGES = 3, TAP_B_OFF = 52 * 1024, TAP_B_BYTES = BN * GEMM_BK * 2;
+  static_assert(!TAP3_OK || (TAP_A_STAGES * TAP_A_BYTES <= TAP_B_OFF && TAP_B_OFF + STAGES * TAP_B_BYTES <= STAGES * SM::STAGE_BYTES),
+                "tap-sharing rings must fit the stage ring");
+  static_assert(2 * STAGES + 5 <= 24, "barrier block");
+  uint64_t* afull = bars + 24;                  // [TAP_A_STAGES]
+  uint64_t* aempty = bars + 27;                 // [TAP_A_STAGES]
+  const bool tap3 = TAP3_OK && p.tap3 != 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -270,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // twice their bytes; the peer's TMA instructions complete_tx on it -- the transaction count may run negative inside
     // a phase), its accumulator-empty barrier collects the epilogue warps of both CTAs; empty / accumulator-full
     // barriers are signalled in both CTAs by multicast commits
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], tap3 ? 1 : 2); mbar_init(&empty_bar[i], 1); }
+    if (tap3) for (int i = 0; i < TAP_A_STAGES; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CG); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
@@ -305,6 +319,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     const uint64_t pol = l2_policy_evict_last();
+    if constexpr (TAP3_OK) if (tap3) {   // chunk-major: the three tap tiles of K chunk c follow each other
+      const int nch = p.seg[0].nchunks;
+      for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int c = 0; c < nch; ++c)
+          for (int t = 0; t < 3; ++t) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sb = smem + TAP_B_OFF + stage * TAP_B_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
+              if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], (t * nch + c) * GEMM_BK, n0, pol);
+              else tma_load_2d(sb, &tmB, &full_bar[stage], (t * nch + c) * GEMM_BK, n0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+    if (!tap3)
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int n0 = (tile % p.n_tiles) * BN;
       for (int kc = 0; kc < total_chunks; kc += KSUB) {
@@ -359,6 +392,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================================== TMA producer: activations ===========================
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (TAP3_OK) if (tap3) {   // one 130-row tile (rows r0 - 1 .. r0 + 128) per K chunk
+      const int nch = p.seg[0].nchunks, col0 = p.seg[0].col0;
+      for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
+        const int r0 = tile_r0(tile);
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(&aempty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
+            tma_load_2d(smem + stage * TAP_A_BYTES, &tmA1, &afull[stage], col0 + c * GEMM_BK, r0 - 1);
+          }
+          __syncwarp();
+          if (++stage == TAP_A_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    if (!tap3)
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int r0 = tile_r0(tile);
       for (int s = 0; s < p.num_segs; ++s) {
@@ -391,6 +440,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    if constexpr (TAP3_OK) if (tap3) {
+      // tap-sharing: K chunk c of the activations is staged once (rows r0 - 1 .. r0 + 128); tap t reads it through a
+      // descriptor that starts t rows (t * 128 B) into the 128B-swizzled tile -- the swizzle is a function of the
+      // shared-memory address bits, so the shifted view addresses exactly the rows TMA wrote
+      const int nch = p.seg[0].nchunks;
+      int sa_i = 0;
+      uint32_t sa_ph = 0;
+      for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(&afull[sa_i], sa_ph);
+          if (p.tl2 && lane == 0 && c == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti] = clock64();
+          for (int t = 0; t < 3; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + sa_i * TAP_A_BYTES) + t * (GEMM_BK * 2));
+            const uint64_t db = umma_desc_sw128(smem_u32(smem + TAP_B_OFF + stage * TAP_B_BYTES));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+              umma_commit(&empty_bar[stage]);
+              if (t == 2) umma_commit(&aempty[sa_i]);
+              if (t == 2 && c + 1 == nch) umma_commit(&tfull_bar[as]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++sa_i == TAP_A_STAGES) { sa_i = 0; sa_ph ^= 1; }
+        }
+        if (p.tl2 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 1] = clock64();
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    if (!tap3)
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       // converged warp: waits by every lane, tcgen05 instructions by one elected lane (uniform operands)
       mbar_wait(&tempty_bar[as], aphase ^ 1);

@@ -100,11 +100,14 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t n
 struct TMap {
   CUtensorMap d2, d3;
   CUtensorMap d2h;   // 2-D with 128-row boxes: a CTA pair's half of a 256-row weight tile (cta_group::2 GEMMs)
+  CUtensorMap d2t;   // activations: 2-D with 130-row boxes, one tile for the three taps of a k3 conv (GemmParams::tap3)
 };
 static int make_tmap(TMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
   if (make_map(&m->d2, base, rows, cols, pitch, box_rows)) return MTTS_ECUDA;
   m->d2h = m->d2;
   if (box_rows == 256 && make_map(&m->d2h, base, rows, cols, pitch, 128)) return MTTS_ECUDA;
+  m->d2t = m->d2;
+  if (box_rows == 128 && make_map(&m->d2t, base, rows, cols, pitch, 130)) return MTTS_ECUDA;
   m->d3 = m->d2;
   if (cols % 128 == 0 && make_map3(&m->d3, base, rows, (uint32_t)(cols / 64), pitch, 128, 2)) return MTTS_ECUDA;
   return 0;
@@ -203,6 +206,7 @@ struct MttsHandle {
   bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   int gn_rpw = 4;           // MTTS_GN_RPW=8: GroupNorm-apply with 8 rows per warp in flight (32 rows per block) instead of 4
+  bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
@@ -600,6 +604,16 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
                                stream, a0.d2, a1.d2, wmap.d2h, pp));
         launched(h);
         return 0;
+      }
+    }
+    if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
+      // k3 conv over ONE source: the three taps share one (128 + 2)-row activation tile per K chunk
+      if (h->tap3 && p.num_segs == 3 && p.res_chunk0 == 0 && p.seg[0].src == 0 && p.seg[1].src == 0 && p.seg[2].src == 0 &&
+          p.seg[0].row_shift == -1 && p.seg[1].row_shift == 0 && p.seg[2].row_shift == 1 && p.seg[0].col0 == p.seg[1].col0 &&
+          p.seg[0].col0 == p.seg[2].col0 && p.seg[0].nchunks == p.seg[1].nchunks && p.seg[0].nchunks == p.seg[2].nchunks) {
+        GemmParams q = p;
+        q.tap3 = 1;
+        return launch_gemm_maps<256, EPI, 1>(h, a0.d2, a0.d2t, wmap.d2, q, stream, aflops);
       }
     }
     return launch_gemm_maps<BN, EPI, 1>(h, a0.d2, a1.d2, wmap.d2, p, stream, aflops);
@@ -1059,6 +1073,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
   if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : atoi(e) == 2 ? 2 : 4;
+  if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');

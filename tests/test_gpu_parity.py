@@ -421,7 +421,7 @@ def test_chains_setting_keeps_results(lj):
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", ["MTTS_GNFUSE", "MTTS_LNQKV", "MTTS_STAGGER", "MTTS_NO_TAIL", "MTTS_NO_PDL", "MTTS_PAIRS",
-                                 "MTTS_ATTN_V1", "MTTS_ATTN_V2", "MTTS_PDL_EARLY", "MTTS_TAIL_PAIRS"])
+                                 "MTTS_ATTN_V1", "MTTS_ATTN_V2", "MTTS_PDL_EARLY", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3"])
 def test_opt_in_variants(env):
     old = os.environ.get(env)
     os.environ[env] = "1"
