@@ -127,9 +127,11 @@ struct GemmParams {
   int a_prefetch;  // 1: L2-prefetch the CTA's first activation tiles before the dependency wait
   int dbg;         // debug experiments (tools/gemm_repeat.py): 1 skip global stores, 2 skip smem staging + stores, 4 skip TMEM loads
   int pdl_late;    // 1: griddepcontrol.launch_dependents when the CTA's last accumulator is complete instead of at entry
-  int tap3;        // 1 (256-wide single-CTA conv tiles only): the three segments are the -1 / 0 / +1 taps of ONE source with the
-                   //    same columns; tmA1 is that source with a 130-row box and one (128 + 2)-row activation tile per K chunk
-                   //    feeds all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu)
+  int tap3;        // n = 1 / 2 (256-wide single-CTA conv tiles only): the segments are the -1 / 0 / +1 taps of n sources (seg[t*n + s],
+                   //    same columns per source), optionally followed by the res_conv segments (shift 0, one per source, K chunks from
+                   //    res_chunk0 on).  tmA0 / tmA1 then have 130-row boxes and one (128 + 2)-row activation tile per K chunk feeds
+                   //    all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu); the res_conv pass
+                   //    stages the tiles once more and reads them one row in
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -319,22 +321,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     const uint64_t pol = l2_policy_evict_last();
-    if constexpr (TAP3_OK) if (tap3) {   // chunk-major: the three tap tiles of K chunk c follow each other
-      const int nch = p.seg[0].nchunks;
+    if constexpr (TAP3_OK) if (tap3) {   // chunk-major: the three tap tiles of a K chunk follow each other; then the res_conv chunks
+      const int nsrc = p.tap3;
+      int CH = 0;
+      for (int q = 0; q < nsrc; ++q) CH += p.seg[q].nchunks;
+      const bool has_res = p.res_chunk0 > 0;
+      auto put = [&](int kc, int n0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sb = smem + TAP_B_OFF + stage * TAP_B_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
+          if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
+          else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         const int n0 = (tile % p.n_tiles) * BN;
-        for (int c = 0; c < nch; ++c)
-          for (int t = 0; t < 3; ++t) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-              uint8_t* sb = smem + TAP_B_OFF + stage * TAP_B_BYTES;
-              mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
-              if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], (t * nch + c) * GEMM_BK, n0, pol);
-              else tma_load_2d(sb, &tmB, &full_bar[stage], (t * nch + c) * GEMM_BK, n0);
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
+        for (int c = 0; c < CH; ++c)
+          for (int t = 0; t < 3; ++t) put(t * CH + c, n0);
+        if (has_res)
+          for (int c = 0; c < CH; ++c) put(p.res_chunk0 + c, n0);
       }
     }
     if (!tap3)
@@ -392,19 +400,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================================== TMA producer: activations ===========================
     int stage = 0;
     uint32_t phase = 0;
-    if constexpr (TAP3_OK) if (tap3) {   // one 130-row tile (rows r0 - 1 .. r0 + 128) per K chunk
-      const int nch = p.seg[0].nchunks, col0 = p.seg[0].col0;
+    if constexpr (TAP3_OK) if (tap3) {   // one 130-row tile (rows r0 - 1 .. r0 + 128) per K chunk and pass
+      const int nsrc = p.tap3;
+      const int passes = p.res_chunk0 > 0 ? 2 : 1;
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         const int r0 = tile_r0(tile);
-        for (int c = 0; c < nch; ++c) {
-          mbar_wait(&aempty[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
-            tma_load_2d(smem + stage * TAP_A_BYTES, &tmA1, &afull[stage], col0 + c * GEMM_BK, r0 - 1);
+        for (int pass = 0; pass < passes; ++pass)
+          for (int q = 0; q < nsrc; ++q) {
+            const GemmSeg sg = p.seg[q];
+            const CUtensorMap* tm = q ? &tmA1 : &tmA0;
+            for (int c = 0; c < sg.nchunks; ++c) {
+              mbar_wait(&aempty[stage], phase ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
+                tma_load_2d(smem + stage * TAP_A_BYTES, tm, &afull[stage], sg.col0 + c * GEMM_BK, r0 - 1);
+              }
+              __syncwarp();
+              if (++stage == TAP_A_STAGES) { stage = 0; phase ^= 1; }
+            }
           }
-          __syncwarp();
-          if (++stage == TAP_A_STAGES) { stage = 0; phase ^= 1; }
-        }
       }
     }
     if (!tap3)
@@ -441,17 +455,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     if constexpr (TAP3_OK) if (tap3) {
-      // tap-sharing: K chunk c of the activations is staged once (rows r0 - 1 .. r0 + 128); tap t reads it through a
+      // tap-sharing: a K chunk of the activations is staged once (rows r0 - 1 .. r0 + 128); tap t reads it through a
       // descriptor that starts t rows (t * 128 B) into the 128B-swizzled tile -- the swizzle is a function of the
-      // shared-memory address bits, so the shifted view addresses exactly the rows TMA wrote
-      const int nch = p.seg[0].nchunks;
+      // shared-memory address bits, so the shifted view addresses exactly the rows TMA wrote.  With a res_conv the
+      // chunks are staged a second time and read one row in (shift 0) into the second accumulator half; the two halves
+      // are handed over separately like in the tap-by-tap order (barrier pairs [0] / [1]).
+      int CH = 0;
+      for (int q = 0; q < p.tap3; ++q) CH += p.seg[q].nchunks;
+      const bool has_res = p.res_chunk0 > 0;
       int sa_i = 0;
       uint32_t sa_ph = 0;
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int c = 0; c < nch; ++c) {
+        for (int c = 0; c < CH; ++c) {
           mbar_wait(&afull[sa_i], sa_ph);
           if (p.tl2 && lane == 0 && c == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti] = clock64();
           for (int t = 0; t < 3; ++t) {
@@ -464,16 +482,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
               umma_commit(&empty_bar[stage]);
               if (t == 2) umma_commit(&aempty[sa_i]);
-              if (t == 2 && c + 1 == nch) umma_commit(&tfull_bar[as]);
+              if (t == 2 && c + 1 == CH) umma_commit(&tfull_bar[has_res ? 0 : as]);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (++sa_i == TAP_A_STAGES) { sa_i = 0; sa_ph ^= 1; }
         }
+        if (has_res) {
+          mbar_wait(&tempty_bar[1], aphase ^ 1);   // the previous tile's res half has been drained
+          tc_fence_after();
+          for (int c = 0; c < CH; ++c) {
+            mbar_wait(&afull[sa_i], sa_ph);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + sa_i * TAP_A_BYTES) + GEMM_BK * 2);   // shift 0 = one row in
+            const uint64_t db = umma_desc_sw128(smem_u32(smem + TAP_B_OFF + stage * TAP_B_BYTES));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem + BN, da + 2 * k, db + 2 * k, idesc, (c | k) != 0);
+              umma_commit(&empty_bar[stage]);
+              umma_commit(&aempty[sa_i]);
+              if (c + 1 == CH) umma_commit(&tfull_bar[1]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++sa_i == TAP_A_STAGES) { sa_i = 0; sa_ph ^= 1; }
+          }
+        }
         if (p.tl2 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 1] = clock64();
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        if (has_res) { aphase ^= 1; }   // dual accumulator: one TMEM stage
+        else { as ^= 1; if (as == 0) aphase ^= 1; }
       }
     }
     if (!tap3)

@@ -206,6 +206,7 @@ struct MttsHandle {
   bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
                            // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
   int gn_rpw = 4;           // MTTS_GN_RPW=8: GroupNorm-apply with 8 rows per warp in flight (32 rows per block) instead of 4
+  bool tap3_plain = true, tap3_res = true;   // MTTS_TAP3=1: only the convs without res_conv, =2: only those with (A/B measurements)
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
@@ -607,13 +608,24 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
       }
     }
     if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
-      // k3 conv over ONE source: the three taps share one (128 + 2)-row activation tile per K chunk
-      if (h->tap3 && p.num_segs == 3 && p.res_chunk0 == 0 && p.seg[0].src == 0 && p.seg[1].src == 0 && p.seg[2].src == 0 &&
-          p.seg[0].row_shift == -1 && p.seg[1].row_shift == 0 && p.seg[2].row_shift == 1 && p.seg[0].col0 == p.seg[1].col0 &&
-          p.seg[0].col0 == p.seg[2].col0 && p.seg[0].nchunks == p.seg[1].nchunks && p.seg[0].nchunks == p.seg[2].nchunks) {
-        GemmParams q = p;
-        q.tap3 = 1;
-        return launch_gemm_maps<256, EPI, 1>(h, a0.d2, a0.d2t, wmap.d2, q, stream, aflops);
+      // k3 conv over one or two sources (+ res_conv): the three taps share one (128 + 2)-row activation tile per K chunk
+      if (h->tap3) {
+        const int nsrc = (p.num_segs == 3 || p.num_segs == 4) ? 1 : ((p.num_segs == 6 || p.num_segs == 8) ? 2 : 0);
+        const bool has_res = nsrc && p.num_segs == 4 * nsrc;
+        bool ok = nsrc > 0 && (has_res || h->tap3_plain);
+        int CH = 0;
+        for (int s = 0; ok && s < nsrc; ++s) CH += p.seg[s].nchunks;
+        for (int t = 0; ok && t < (has_res ? 4 : 3); ++t)
+          for (int s = 0; ok && s < nsrc; ++s) {
+            const GemmSeg& g = p.seg[t * nsrc + s];
+            ok = g.src == s && g.row_shift == (t < 3 ? t - 1 : 0) && g.col0 == p.seg[s].col0 && g.nchunks == p.seg[s].nchunks;
+          }
+        ok = ok && p.res_chunk0 == (has_res ? 3 * CH : 0) && (!has_res || h->tap3_res);
+        if (ok) {
+          GemmParams q = p;
+          q.tap3 = nsrc;
+          return launch_gemm_maps<256, EPI, 1>(h, a0.d2t, nsrc == 2 ? a1.d2t : a0.d2t, wmap.d2, q, stream, aflops);
+        }
       }
     }
     return launch_gemm_maps<BN, EPI, 1>(h, a0.d2, a1.d2, wmap.d2, p, stream, aflops);
@@ -1074,6 +1086,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
   if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : atoi(e) == 2 ? 2 : 4;
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_TAP3")) { h->tap3_plain = (e[0] != '2'); h->tap3_res = (e[0] != '1'); }
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');
