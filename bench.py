@@ -10,13 +10,17 @@ decoder, B=64 utterances x T_mel=344 frames, random-init weights, synthetic mu /
           lane (CUDA stream + native handle), the way a serving process overlaps consecutive batches: one solve is a
           serial chain of ~490 latency-bound kernels, a second one fills the SMs it leaves idle.  Timed with CUDA
           events around all K steps, max over ranks; the steps rotate over distinct input sets larger than L2.
-          config.serial holds the one-solve-at-a-time figure (L2 flushed between steps).
+          config.serial holds the one-solve-at-a-time figure (L2 flushed between steps), config.sustained the same
+          loop over 120 steps (under the power cap).
   e2e   : the same metric through the public API CFM.forward(mu, mask, n_timesteps, temperature)
           with mu/mask in pinned HOST memory and the mel read back to the host every step.
   roofline : tcgen05 GEMM kernel (all convs + linears): algorithmic FLOPs / CUDA-event time of its
           launches inside one solve, against the measured sustained bf16 peak.
-  cpu_baseline : the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1).
-`--impl reference` times only that CPU port (bounded sample of the same workload) and prints the
+  cpu_baseline : the reference's own CFM.forward (baseline/_ref/model.py, staged by tools/stage_reference.sh; the oracle
+          port if it is not staged) on this box's host cores (rank 0, N=1): a bounded sample of the workload + config 1.
+  config5 : BASELINE config 5 (4096 multi-speaker utterances, bucketed, sharded over the ranks, NCCL gather included).
+  reference_on_gpu : informative -- the unmodified reference through PyTorch eager on the same GPU (N=1).
+`--impl reference` times only the CPU path (bounded sample of the same workload) and prints the
 same JSON shape with "impl": "reference".
 """
 import argparse
@@ -90,36 +94,122 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU port of the reference path (oracle) -- used for cpu_baseline and for --impl reference
+# CPU baseline: the reference's OWN implementation when it is staged (baseline/_ref/model.py, copied by
+# tools/stage_reference.sh; git-ignored, travels with the gpurun snapshot), else the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(B, T, n_timesteps, steps, warmup, budget_s):
+def load_reference():
+    """The reference's model.py (CFM.forward :1136, BASECFM Euler loop :1084-1109, Decoder :834-1048) or None."""
+    path = os.path.join(ROOT, "baseline", "_ref", "model.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location("matcha_reference_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_cfm(ref, device="cpu"):
+    """The reference's CFM around its Decoder with the hyper-parameters of reference main.py:67-75, seed 0, eval()."""
     import torch
-    from oracle import cfm_oracle as O
+    torch.manual_seed(0)
+    dec = ref.Decoder(in_channels=160, out_channels=80, channels=(256, 256), dropout=0.05, attention_head_dim=64,
+                      n_blocks=1, num_mid_blocks=2, num_heads=2, act_fn="snakebeta")
+    return ref.CFM(80, {"solver": "euler", "sigma_min": 1e-4}, estimator=dec).eval().to(device)
+
+
+def cpu_reference(B, T, n_timesteps, steps, warmup, budget_s):
+    """Times the CPU path on a bounded sample (rows of the B x T batch) with every host thread torch will use.
+    kind = "reference": reference CFM.forward from baseline/_ref; kind = "port": oracle.euler_solve."""
+    import torch
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    cfg = O.DecoderCfg()
-    sd = O.make_state_dict(cfg, 0)
-    # size the sample (rows of the B x T batch) so that (steps + warmup) solves fit the budget
-    mu, mask, z0, _ = O.make_inputs(cfg, 1, T, None, seed=1)
-    with torch.inference_mode():
-        O.euler_solve(sd, cfg, z0, mu, mask, 1)                       # page in / thread pool start
+    ref = load_reference()
+    if ref is not None:
+        cfm = reference_cfm(ref)
+        kind = "reference"
+
+        def make(rows):
+            g = torch.Generator().manual_seed(1)
+            return torch.randn(rows, 80, T, generator=g), torch.ones(rows, 1, T)
+
+        def solve(inp, n):
+            cfm(inp[0], inp[1], n, temperature=0.667)
+    else:
+        from oracle import cfm_oracle as O
+        cfg = O.DecoderCfg()
+        sd = O.make_state_dict(cfg, 0)
+        kind = "port"
+
+        def make(rows):
+            mu, mask, z0, _ = O.make_inputs(cfg, rows, T, None, seed=1)
+            return mu, mask, z0
+
+        def solve(inp, n):
+            with torch.inference_mode():
+                O.euler_solve(sd, cfg, inp[2], inp[0], inp[1], n)
+    # SURVEY.md section 8(d) config 1: B=1 x T, 1 warm-up, best of 5
+    one = make(1)
+    solve(one, 1)                                                     # page in / thread pool start
+    solve(one, n_timesteps)
+    t1 = []
+    for _ in range(5):
         t0 = time.perf_counter()
-        O.euler_solve(sd, cfg, z0, mu, mask, n_timesteps)
-        t_row = time.perf_counter() - t0
-    rows = int(max(1, min(16, B, budget_s / max(1, steps + warmup) / t_row)))
-    mu, mask, z0, _ = O.make_inputs(cfg, rows, T, None, seed=1)
+        solve(one, n_timesteps)
+        t1.append(time.perf_counter() - t0)
+    config1 = {"batch": 1, "t_mel": T, "seconds_best_of_5": min(t1), "value": T / min(t1), "unit": UNIT}
+    # the line's value: a bounded sample of the B x T workload, sized so that (steps + warmup) solves fit the budget
+    rows = int(max(1, min(16, B, budget_s / max(1, steps + warmup) / min(t1))))
+    inp = make(rows)
     times = []
-    with torch.inference_mode():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            O.euler_solve(sd, cfg, z0, mu, mask, n_timesteps)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        solve(inp, n_timesteps)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
     mean = sum(times) / len(times)
-    return {"value": rows * T / mean, "ms_per_step": mean * 1e3, "cores": cores, "rows": rows,
-            "sample": f"{rows} of {B} rows x T={T}, {n_timesteps} Euler steps, fp32 torch-CPU, "
+    what = ("reference CFM.forward (baseline/_ref/model.py, unmodified)" if kind == "reference"
+            else "oracle port of the reference PyTorch path (baseline/_ref not staged)")
+    return {"value": rows * T / mean, "ms_per_step": mean * 1e3, "cores": cores, "rows": rows, "kind": kind, "config1": config1,
+            "sample": f"{what}: {rows} of {B} rows x T={T}, {n_timesteps} Euler steps, fp32 torch-CPU on {cores} threads, "
                       f"{steps} timed solves after {warmup} warm-up (mean)"}
+
+
+def reference_on_gpu(B, T, n_timesteps, dev, reps=3):
+    """Informative (SURVEY.md section 2.1 / BASELINE.md section 2): the unmodified reference through PyTorch eager on this
+    B200 -- fp32 with torch's default TF32 convolutions, and autocast(bfloat16) -- "the library kernels to beat"."""
+    import torch
+    ref = load_reference()
+    if ref is None:
+        return None
+    cfm = reference_cfm(ref, dev)
+    g = torch.Generator().manual_seed(1)
+    mu = torch.randn(B, 80, T, generator=g).to(dev)
+    mask = torch.ones(B, 1, T, device=dev)
+    out = {}
+    for name, ctx in (("eager_fp32_tf32conv", None), ("autocast_bf16", torch.bfloat16)):
+        try:
+            def run():
+                if ctx is None:
+                    return cfm(mu, mask, n_timesteps, temperature=0.667)
+                with torch.autocast("cuda", dtype=ctx):
+                    return cfm(mu, mask, n_timesteps, temperature=0.667)
+            run()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                z = run()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"value": B * T / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms, "finite": bool(torch.isfinite(z).all())}
+        except Exception as exc:      # an eager-path failure must not take the bench line down
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    out["note"] = f"reference CFM.forward, PyTorch eager on the same GPU, batch {B} x T={T}, {n_timesteps} steps, mean of {reps}"
+    return out
 
 
 def run_reference(args):
@@ -131,13 +221,29 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, extra={"device": "host CPU", "note": "oracle port of the reference PyTorch "
-                                               "path (reference is pure Python/PyTorch; no compiled artefact)"}),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": workload_config(args, extra={"device": "host CPU", "config1_cpu": r["config1"],
+                                               "note": "the reference's CPU PyTorch path on this box's host cores, one process "
+                                                       "(it does not shard); the reference is pure Python/PyTorch, nothing compiled"}),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+def traffic_from_profiles():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed from the committed summary
+    of this round's `ncu --set full` capture (profiles/roofline_traffic.json names the capture it came from); None when
+    no current capture is committed."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        d = json.load(open(path))
+        return {"bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"], "kernel": d["kernel"], "source": d["source"],
+                "algorithmic_bytes_per_launch": d.get("algorithmic_bytes")}
+    except Exception:
+        return None
 
 
 def workload_config(args, extra=None):
@@ -283,6 +389,21 @@ def run_native(args):
         total_ms = float(t.item())
     value = frames / (total_ms * 1e-3)
 
+    # ---- the same loop over >= 120 steps: the sustained figure under the power cap (the K-step region above is a burst) ----
+    sustained = None
+    if args.sustained_steps > 0:
+        with torch.cuda.stream(stream):
+            barrier()
+            s0, s1 = run_lanes(args.sustained_steps)
+            barrier()
+            sus_ms = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([sus_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_ms = float(t.item())
+        sustained = {"steps": args.sustained_steps, "value": world * B * T * args.sustained_steps / (sus_ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": sus_ms / args.sustained_steps}
+
     # ---- end to end through the public API: pinned host inputs -> CFM.forward -> host mel ----
     # Every step copies its own inputs host->device and its result device->host inside the timed region.
     # The loop is pipelined the way a serving process is: the copies of step i+1 / i-1 run on copy streams
@@ -357,10 +478,7 @@ def run_native(args):
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel + ff_tail_kernel (tcgen05 implicit GEMMs: all convs + linears)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": f"{which} sustained bf16 (MEASURED_PEAKS.json); fp16 runs at the same tcgen05 rate",
-                # dram__bytes_read + dram__bytes_write of the block2 conv launch at level T (8.66 GFLOP), one
-                # `ncu --set full` capture: profiles/r01c_ncu_stage0_summary.txt (cold L2 under ncu; the
-                # algorithmic bytes of that launch are 11.3 MB in + 11.3 MB out + 0.4 MB weights)
-                "traffic": 11.86e6,
+                "traffic": traffic_from_profiles(),
                 "avg_launch_us": gm["ms"] * 1e3 / gm["launches"], "launches_per_solve": gm["launches"],
                 "algorithmic_flop_per_solve": gm["flop"],
                 "share_of_solve": {k: round(v["ms"] / sum(x["ms"] for x in kinds.values()), 4) for k, v in kinds.items()},
@@ -421,12 +539,30 @@ def run_native(args):
                                 "achieved": tf_k, "peak": burst, "unit": "TFLOP/s", "frac": tf_k / burst,
                                 "note": f"{reps_k} back-to-back launches over the {rows_k} rows of {F} in-flight solves; burst bf16 peak"}
 
+    # ---- BASELINE config 5 folded into the line: 4096 multi-speaker utterances, bucketed, sharded over the ranks (strong
+    #      scaling), the NCCL gather of the mels included, SHA-256 over all mels (equal for every N) ----
+    config5 = None
+    if not args.no_config5:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config5 as c5
+        del lane_sets, lane_gather, mu_dv, mask_dv
+        torch.cuda.empty_cache()
+        try:
+            config5 = c5.run(dev, world, rank, n_utt=args.config5_utts, max_frames=args.config5_frames, lanes=args.config5_lanes)
+        except Exception as exc:                                   # never take the headline line down
+            config5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    ref_gpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ref_gpu = reference_on_gpu(B, T, n, dev)
+
     if rank == 0:
         flop_step = B * T * n * (GEMM_FLOP_PER_FRAME_STEP + ATTN_FLOP_PER_FRAME_STEP_PER_T * T)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(B, T, n, steps=3, warmup=1, budget_s=25.0)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "config1": r["config1"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -437,9 +573,10 @@ def run_native(args):
                 "in_flight_solves": F, "chains_per_solve": 1 if F > 1 else "heuristic (2)",
                 "l2": f"steps rotate over {F * NSET} distinct (mu, z0, z) sets = {set_bytes / 2**20:.0f} MiB > 126 MB L2, and every solve "
                       f"streams its own {eng.workspace(B, T)[2] / 2**20:.0f} MiB workspace; the serial figure flushes L2 (256 MiB write) between steps",
+                "sustained": sustained,
                 "serial": {"value": serial_value, "ms_per_step": serial_ms / args.steps, "ms_min": min(ms), "ms_max": max(ms),
                            "note": "one solve at a time (latency of a batch-64 solve), L2 flushed between steps"}}),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "config5": config5, "reference_on_gpu": ref_gpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": mu_h.numel() * 4 + mask_h.numel() * 4,
                     "d2h_bytes_per_step": out_h[0].numel() * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "CFM.forward(mu, mask, n_timesteps, temperature) per step, pinned-host mu/mask in and mel out per step; "
@@ -464,6 +601,11 @@ def main():
     ap.add_argument("--ragged", action="store_true")
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "3")), help="independent solves (batches) in flight at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=120, help="extra timed region of this many steps (0 = skip)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 job folded into the line")
+    ap.add_argument("--config5-utts", type=int, default=4096)
+    ap.add_argument("--config5-frames", type=int, default=64 * 344, help="padded-frame budget per bucket")
+    ap.add_argument("--config5-lanes", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

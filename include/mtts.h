@@ -75,7 +75,8 @@ int mtts_load_weight(MttsHandle* h, int idx, const float* dev_src, int64_t numel
 int mtts_weights_loaded(const MttsHandle* h); /* 1 when every table entry has been loaded */
 
 /* ---- workspace ----------------------------------------------------------------------------- */
-/* Bytes of scratch needed for a batch of B utterances padded to T frames (T even, T >= 2).
+/* Bytes of scratch needed for a batch of B utterances padded to T frames (1 <= B <= 2048, T >= 1; odd T follows the
+ * reference's nearest-resize crop after the ConvTranspose, model.py:1027-1028).
  * Returns 0 on invalid shapes. */
 size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T);
 

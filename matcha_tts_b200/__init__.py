@@ -7,6 +7,8 @@ from .model import (BASECFM, CFM, Decoder, MatchaTTS, denormalize, fix_len_compa
                     sequence_mask)
 
 from . import batching  # noqa: E402,F401  (length bucketing + utterance sharding front end)
+from . import checkpoint  # noqa: E402,F401  (Lightning checkpoint load, flat weight file, mel writer)
+from .checkpoint import load_lightning_checkpoint  # noqa: E402
 
-__all__ = ["batching", "BASECFM", "CFM", "Decoder", "MatchaTTS", "denormalize", "fix_len_compatibility", "generate_path",
+__all__ = ["batching", "checkpoint", "load_lightning_checkpoint", "BASECFM", "CFM", "Decoder", "MatchaTTS", "denormalize", "fix_len_compatibility", "generate_path",
            "sequence_mask"]

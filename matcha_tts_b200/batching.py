@@ -11,7 +11,9 @@ the attention-mask quirk keys on padding: SURVEY.md section 0, traps 5 and 6), s
 
 Buckets are then assigned to ranks (one process per GPU) by greedy longest-processing-time on the
 padded-frame cost B*T*F(T); each rank solves its own buckets with no collective on the hot path and
-the finished mels are gathered once at the end (torch.distributed all_gather_object / NCCL or gloo).
+the finished mels are gathered once at the end: ONE all_gather_into_tensor (ncclAllGather over NVLink; gloo in the
+CPU tests) of each rank's compacted frames arena.  No lengths travel: the bucket -> rank assignment is a deterministic
+function of the length list, so every rank knows every other rank's utterances, their order and their frame counts.
 """
 from __future__ import annotations
 
@@ -124,20 +126,22 @@ class MelDict(dict):
             self.clear()
 
 
-def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[int, torch.Tensor]:
+def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes, keep_device=False):
     """CUDA path of solve_sharded.  Host work per bucket is a handful of launches, whatever the batch size:
       * the local utterances are concatenated ONCE into a frames table (n_feats, total + 1), last column zero;
       * padding a bucket is one index_select with indices computed on the host for all buckets at once (numpy) and
         uploaded in one non-blocking copy from pinned memory -- no per-utterance slice copies, no synchronising
         torch.tensor(..., device=cuda); the mask comes from the same indices; speaker rows are slices of one stack;
       * the solved mel is compacted to its valid frames on the GPU and lands in one pinned arena; the result dict
-        holds views into it (no per-utterance host copies)."""
+        holds views into it (no per-utterance host copies).
+    keep_device: the compacted frames stay in ONE device arena (total, n_feats), returned as (arena, local_ids) for the
+    final gather instead of a host dict."""
     import numpy as np
     n_feats = int(mus[0].shape[0]) if len(mus) else 0
     local_ids = [i for bid in mine for i in buckets[bid].indices]
     out = MelDict()
     if not local_ids:
-        return out
+        return (torch.zeros(0, n_feats, device=dev), local_ids) if keep_device else out
     lens = np.asarray([lengths[i] for i in local_ids], dtype=np.int64)
     offs = np.concatenate([[0], np.cumsum(lens)])                # frame offset of every local utterance in the table
     total = int(offs[-1])
@@ -153,7 +157,7 @@ def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[i
     plan_h = _pinned_i64(pos)
     plan_h[:pos].copy_(torch.from_numpy(flat_plan))
     plan_d = plan_h[:pos].to(dev, non_blocking=True)
-    arena = _pinned_arena(total * n_feats).view(total, n_feats)
+    arena = torch.empty(total, n_feats, device=dev) if keep_device else _pinned_arena(total * n_feats).view(total, n_feats)
     streams = _lane_streams(dev, lanes) if lanes > 1 else [cur]
     done = []
     for k, (bk, r0, i0, i1, i2, f0, nv) in enumerate(plan):
@@ -175,6 +179,11 @@ def _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, lanes) -> Dict[i
     for ev in done:
         ev.synchronize()
     _PINNED.setdefault(("i64", plan_h.numel()), []).append(plan_h)
+    if keep_device:
+        for ls in streams:                                         # the gather runs on the caller's stream
+            if ls is not cur:
+                cur.wait_stream(ls)
+        return arena, local_ids
     for j, i in enumerate(local_ids):
         out[i] = arena[int(offs[j]):int(offs[j + 1])].t()          # (n_feats, T_i) view
     out.arena = arena
@@ -260,12 +269,13 @@ Solver = Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Bucket], 
 
 def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Sequence[torch.Tensor]] = None,
                   max_frames: int = 64 * 344, max_batch: int = 256, device=None, group=None,
-                  gather: bool = True, lanes: int = 1) -> Dict[int, torch.Tensor]:
+                  gather=True, lanes: int = 1) -> Dict[int, torch.Tensor]:
     """Run `solver(mu, mask, spks, bucket) -> (B, n_feats, T_max)` over this rank's buckets and gather.
 
     mus[i]: (n_feats, T_i) encoder output of utterance i (every rank passes the same list; only the
     local shard is touched).  Returns {utterance index: (n_feats, T_i) mel on the CPU}; with
-    `gather` every rank gets all utterances, otherwise only its own.
+    `gather` (True / "host") every rank gets all utterances, with "rank0" only rank 0 copies them to its host, with
+    "device" they stay views of the gathered device arena; False returns the local shard only.
     In production `solver` is `lambda mu, mask, s, b: cfm(mu, mask, n_timesteps, temperature, s)`
     (matcha_tts_b200.CFM); the CPU tests inject a stub, the scheduling/gather logic is the same.
     `lanes` > 1 (CUDA only) keeps that many buckets in flight on as many CUDA streams -- every stream has its own
@@ -285,8 +295,13 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
             local[i] = out[row, :, :lengths[i]].clone()
 
     dev = torch.device(device) if device is not None else None
-    if dev is not None and dev.type == "cuda":
-        local = _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, max(1, lanes))
+    cuda = dev is not None and dev.type == "cuda"
+    do_gather = use_dist and bool(gather) and world > 1
+    n_feats = int(mus[0].shape[0]) if len(mus) else 0
+    if cuda and do_gather:
+        arena, local_ids = _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, max(1, lanes), keep_device=True)
+    elif cuda:
+        return _solve_cuda(mus, solver, spks, buckets, mine, lengths, dev, max(1, lanes))
     else:
         for bid in mine:
             bk = buckets[bid]
@@ -296,13 +311,43 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
                 s = torch.stack([spks[i] for i in bk.indices]).to(device=device, dtype=torch.float32)
             out = solver(mu, mask, s, bk)
             unpack(bk, out.detach().to("cpu", torch.float32))
-    if not (use_dist and gather and world > 1):
-        return local
-    if isinstance(local, MelDict):                          # views of one arena: pickle each utterance on its own
-        local = {i: v.contiguous() for i, v in local.items()}
-    parts: List[Optional[dict]] = [None] * world
-    dist.all_gather_object(parts, local, group=group)      # the only collective: finished mels
-    merged: Dict[int, torch.Tensor] = {}
-    for p in parts:
-        merged.update(p)
-    return merged
+        if not do_gather:
+            return local
+        local_ids = [i for bid in mine for i in buckets[bid].indices]
+        arena = (torch.cat([local[i].t() for i in local_ids], dim=0) if local_ids else torch.zeros(0, n_feats))
+    return _gather_frames(arena, buckets, lengths, world, rank, group, n_feats, gather)
+
+
+def _gather_frames(arena: torch.Tensor, buckets, lengths, world: int, rank: int, group, n_feats: int, mode):
+    """The final mel gather: every rank contributes its compacted frames arena (frames of its utterances in bucket
+    order, frames-major), padded to the longest arena, through ONE all_gather_into_tensor.  mode: True / "host" -- every
+    rank returns {utterance: (n_feats, T_i)} on the CPU; "rank0" -- only rank 0 copies the gathered frames to the host
+    (the others return {}); "device" -- views of the gathered device arena."""
+    import torch.distributed as dist
+    assign = assign_buckets(buckets, world)
+    ids = [[i for bid in assign[r] for i in buckets[bid].indices] for r in range(world)]
+    totals = [sum(lengths[i] for i in ids_r) for ids_r in ids]
+    assert arena.shape[0] == totals[rank], "frames arena does not match the deterministic assignment"
+    mx = max(max(totals), 1)
+    send = arena.new_zeros(mx, n_feats)
+    send[:totals[rank]].copy_(arena)
+    recv = arena.new_empty(world * mx, n_feats)
+    try:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    except (RuntimeError, NotImplementedError):                  # a backend without the flat form (older gloo)
+        dist.all_gather(list(recv.view(world, mx, n_feats).unbind(0)), send, group=group)
+    out = MelDict()
+    if mode == "rank0" and rank != 0:
+        return out
+    if recv.is_cuda and mode != "device":
+        host = _pinned_arena(recv.numel()).view(world * mx, n_feats)
+        host.copy_(recv, non_blocking=True)
+        torch.cuda.current_stream(recv.device).synchronize()
+        out.arena = host
+        recv = host
+    for r, ids_r in enumerate(ids):
+        off = r * mx
+        for i in ids_r:
+            out[i] = recv[off:off + lengths[i]].t()
+            off += lengths[i]
+    return out

@@ -1,9 +1,16 @@
-// Masked self-attention of BasicTransformerBlock (reference model.py:670-705), 2 heads x 64 -- third generation.
+// Masked self-attention of BasicTransformerBlock (reference model.py:670-705), 2 heads x 64.
 //
-// Same tiling, shared-memory / tensor-memory plan and tcgen05 instruction stream as attention2.cuh (one CTA per
-// (128-query tile, head, utterance), key/value tiles up to 192 keys wide, V read as an MN-major B operand, two CTAs per
-// SM), but the softmax -- the part of attention2 that bounds it: one thread walks a whole 344-key row through two passes
-// over tensor memory with 8 warps per SM to hide the latencies -- is spread over TWO threads per query row:
+// One CTA per (128-query tile, head, utterance), two CTAs per SM.
+//   * key/value tiles are up to 192 keys wide (KT = the utterance's frames split evenly, a multiple of 16): T/2-level
+//     utterances (172 frames at T=344) need ONE tile -- plain softmax, no online rescaling -- and level-T ones two;
+//   * V stays row-major [rows][64] like K: the P V product reads it as an MN-major B operand (instruction-descriptor
+//     bit 16), 16 key rows per K16 step;
+//   * K and V are single-buffered: the next K tile is fetched as soon as S = Q K^T has completed, the next V tile as
+//     soon as O_j = P_j V_j has, so the loads overlap the softmax of the current tile (112 KB -> two CTAs per SM).
+// S and O_j accumulate in TMEM (192 + 64 columns); the un-normalised probabilities go as fp16 into 128B-swizzled smem
+// tiles (A operand of P V) and a register accumulator is rescaled between tiles.  q is pre-scaled by head_dim^-0.5
+// (folded into to_q's packed weight).  The softmax is spread over TWO threads per query row (one thread per row
+// executed 14 instructions per score at 1.8 IPC: issue-bound, profiles/r01i_ncu_attention3_first.txt):
 //   * 256 threads: warps w and w+4 share TMEM lane quarter w%4; warp half 0 owns the S columns [0, c0), half 1 the
 //     columns [c0, KT) (c0 = the multiple of 32 nearest to KT/2 from above), and the O columns [0,32) / [32,64);
 //   * the row maximum is combined through 512 bytes of shared memory (half 0 writes, half 1 merges and writes back),
@@ -17,10 +24,33 @@
 #pragma once
 #include <cuda.h>
 
-#include "attention2.cuh"
 #include "ptx.cuh"
 
 namespace mtts {
+
+constexpr int ATT2_KT_MAX = 192;
+// Q 16 KB | K 24 KB | V 24 KB | P 3 x 16 KB | barriers: two CTAs fit one SM (2 x (112.1 KB + 1 KB) <= 228 KB)
+constexpr int ATT2_OFF_K = 16384;
+constexpr int ATT2_OFF_V = ATT2_OFF_K + ATT2_KT_MAX * 128;
+constexpr int ATT2_OFF_P = ATT2_OFF_V + ATT2_KT_MAX * 128;
+constexpr int ATT2_OFF_BAR = ATT2_OFF_P + 3 * 16384;
+
+struct Attn2Params {
+  int L;      // frames per utterance at this level
+  int Lp;     // rows per utterance in the flat row space (L + guard)
+  int KT;     // keys per tile (multiple of 16, <= 192); the K / V tensor maps have KT-row boxes
+  int nkv;    // key tiles per utterance: ceil(L / KT)
+  const float* rowmask;  // flat per-row mask (0 on guard rows)
+  const int* npad;       // [B] number of frames with mask == 0
+  const __half* v;       // [rows][128] (quirk path)
+  __half* out;           // [rows][128]
+  int pdl_late;          // 1: release the dependent launch after the key/value loop instead of at entry
+};
+
+// instruction descriptor with an MN-major B operand (V: keys x dims, dims contiguous)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(uint32_t M, uint32_t N) {
+  return umma_idesc_f16(M, N) | (1u << 16);
+}
 
 constexpr int ATT3_THREADS = 256;
 constexpr int ATT3_OFF_X = ATT2_OFF_BAR + 64;          // [128] floats: row-maximum exchange
@@ -28,8 +58,8 @@ constexpr int ATT3_SMEM = ATT3_OFF_X + 512;
 static_assert(2 * (ATT3_SMEM + 1024) <= 233472, "two attention CTAs per SM");
 
 
-// one chunk of N S columns held in registers.  MASK = false: every column is a valid key (no per-element predicates --
-// attention2 spent 14 instructions per score, most of them key-validity selects); MASK = true: columns >= lim are excluded
+// one chunk of N S columns held in registers.  MASK = false: every column is a valid key (no per-element predicates);
+// MASK = true: columns >= lim are excluded
 template <int N, bool MASK>
 __device__ __forceinline__ float att3_chunk_max(const float* s, int lim, float mx) {
   if constexpr (MASK) {

@@ -11,13 +11,13 @@ namespace mtts {
 
 // ---------------------------------------------------------------------------------------------
 // mask (B,T) float -> flat per-row masks / utterance ids for both U-Net levels, masked-key counts
-// level T : row b*(T+2)+t, guard rows t in {T, T+1};  level H = T/2: row b*(H+1)+m, guard row m = H,
+// level T : row b*LpT+t, guard rows t in [T, LpT);  level H = ceil(T/2): row b*LpH+m, guard row m = H,
 // mask_H[b,m] = mask[b, 2m]  (reference model.py:1003  mask_down[:, :, ::2])
 // ---------------------------------------------------------------------------------------------
-__global__ void mask_prep_kernel(const float* __restrict__ mask, int T, float* __restrict__ mT,
+__global__ void mask_prep_kernel(const float* __restrict__ mask, int T, int H, int LpT, int LpH, float* __restrict__ mT,
                                  float* __restrict__ mH, int* __restrict__ rowbT, int* __restrict__ rowbH,
                                  int* __restrict__ npadT, int* __restrict__ npadH) {
-  const int b = blockIdx.x, H = T / 2, LpT = T + 2, LpH = H + 1;
+  const int b = blockIdx.x;
   __shared__ int cT, cH;
   if (threadIdx.x == 0) { cT = 0; cH = 0; }
   __syncthreads();
@@ -45,10 +45,10 @@ __global__ void mask_prep_kernel(const float* __restrict__ mask, int T, float* _
 // (reference model.py:975-979 cat + the x*mask of Block1D / res_conv, :774, :789)
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_x0_kernel(const float* __restrict__ z, const float* __restrict__ mu,
-                               const float* __restrict__ spks, const float* __restrict__ mT, int T, int nf,
+                               const float* __restrict__ spks, const float* __restrict__ mT, int T, int LpT, int nf,
                                int nspk, int cinp, __half* __restrict__ x0, int z_only) {
   extern __shared__ float tile[];  // [cinp][33]
-  const int b = blockIdx.y, t0 = blockIdx.x * 32, LpT = T + 2;
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int t = t0 + lane;
   const float m = (t < T) ? mT[(size_t)b * LpT + t] : 0.f;
@@ -98,8 +98,9 @@ struct GnParams {
 };
 
 constexpr int GN_THREADS = 128;       // 4 warps
-// RPW rows per warp, all in flight at once (4 warps: 4 * RPW rows per block)
-template <int MODE, int RPW = 4>
+constexpr int GN_RPW = 4;             // rows per warp, all in flight at once (2 and 8 measured slower: profiles/r01i_variants.txt)
+constexpr int GN_ROWS = 4 * GN_RPW;   // rows per block
+template <int MODE>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) {
   pdl_launch_dependents();
   const int b = blockIdx.y;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   pdl_wait();
   // 1) issue every global load of this block up front (rows, time embedding, statistics partials):
   //    one memory round trip instead of three dependent ones
+  constexpr int RPW = GN_RPW;
   const int tw0 = (blockIdx.x * 4 + warp) * RPW;
   uint4 yv[RPW], rv[RPW];
   float m[RPW];

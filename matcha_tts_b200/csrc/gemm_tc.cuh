@@ -28,9 +28,7 @@
 //   EPI_STATS  +bias, fp16 store, deterministic GroupNorm partial sums per (utterance, group); optionally a
 //              second accumulator fed by extra K chunks of the same A tiles (the ResnetBlock1D 1x1 res_conv)
 //   EPI_PLAIN  +bias (+residual) (*row mask), fp16 store
-//   EPI_LN     +bias +residual -> fp16 store, then LayerNorm(256) of the same row -> second fp16 store
-//   EPI_SNAKE  +bias, SnakeBeta, fp16 store
-//   EPI_QKV    q | k row-major, v transposed per (utterance, head) for the attention kernel
+//   EPI_QKV    q | k | v row-major per head for the attention kernel
 //   EPI_FINAL  final 1x1 projection * mask, Euler update of the fp32 state z (channels-first) and
 //              refresh of the z channels of the first conv's operand buffer
 #pragma once
@@ -49,10 +47,8 @@ constexpr int GEMM_THREADS = 96 + 32 * GEMM_EPI_WARPS;        // 352: A producer
 constexpr int GEMM_MAX_SEGS = 9;
 constexpr int GEMM_STAGING_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 32 fp16, swizzled
 
-enum { EPI_STATS = 0, EPI_PLAIN = 1, EPI_LN = 2, EPI_SNAKE = 3, EPI_QKV = 4, EPI_FINAL = 5, EPI_GNA = 6, EPI_GNB = 7 };
-__host__ __device__ constexpr bool epi_is_gn(int e) { return e == EPI_GNA || e == EPI_GNB; }
-__host__ __device__ constexpr bool epi_has_stats(int e) { return e == EPI_STATS || epi_is_gn(e); }
-constexpr int GEMM_GN_MAXU = 8;   // utterances one 128-row tile may touch in the fused GroupNorm epilogues
+enum { EPI_STATS = 0, EPI_PLAIN = 1, EPI_QKV = 4, EPI_FINAL = 5 };
+__host__ __device__ constexpr bool epi_has_stats(int e) { return e == EPI_STATS; }
 
 struct GemmSeg {
   int src;        // 0/1: which A tensor map
@@ -84,33 +80,10 @@ struct GemmParams {
   int res_chunk0;       // 0 = no second GEMM
   const float* res_bias;
   __half* res_out;      // [row*ldo + n]
-  // EPI_GNA / EPI_GNB: the GroupNorm that follows the conv is finished inside the conv launch.  After a tile's partial
-  // sums are in stats_part the CTA publishes flags[row tile] and waits for the flags of every row tile that holds rows
-  // of its utterances (all CTAs of the launch are co-resident: grid <= #SMs), then normalises the accumulator it still
-  // holds in TMEM:  GNA: out = (Mish(GN(acc+bias))*m + temb)*m          (Block1D + time embedding, model.py:773-775,:786)
-  //                 GNB: out = Mish(GN(acc+bias))*m + resid ; out2 = LayerNorm1(out)      (:773-775, :789, :735)
-  int* flags;           // [row tiles] of this launch, all zero at launch
-  int* flags_clear;     // the other flag array (zeroed here for the next fused launch)
-  int nflags;
-  int L;                // valid frames per utterance (GroupNorm count = 32 * L)
-  int nutt;             // utterances in the row space
-  const float* gn_g;    // GroupNorm affine [256]
-  const float* gn_b;
-  const float* temb;    // GNA: temb[(t_off + b*t_stride)*t_ld + col] or null
-  int t_off, t_stride, t_ld;
-  // EPI_LN
-  const float* ln_g;
-  const float* ln_b;
-  __half* out2;
-  // EPI_SNAKE
-  const float* sn_a;   // exp(alpha) [N]
-  const float* sn_ib;  // 1/(exp(beta)+1e-9) [N]
   // EPI_QKV
   __half* q;
   __half* k;
-  __half* vt;  // [(b*2+h)*64 + d][Lpad]  (first-generation attention kernel)
-  __half* v;   // [rows][128] row-major like q / k (attention2.cuh); when set, vt is not written
-  int Lpad;
+  __half* v;   // [rows][128] row-major like q / k
   // EPI_FINAL
   float* zout;         // (B, n_valid, T) channels-first fp32
   const float* zbase;  // same layout or null
@@ -150,13 +123,9 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (CG == 2) ? 6 : ((BN == 256) ? 4 : (KSUB == 2 ? 3 : 4));
   // per-column epilogue parameters of ALL n-tiles, staged once per CTA: [bias | p1 | p2] x PAR_N
-  static constexpr int PAR_N = (EPI == EPI_LN) ? 256 : (BN == 128 ? 512 : 1024);  // max N of one launch
-  // GN variants: bias | res_bias | gn gamma | gn beta | ln gamma | ln beta, 256 floats each
-  static constexpr int PAR_BYTES = epi_is_gn(EPI) ? 6 * 256 * 4 : ((EPI == EPI_SNAKE || EPI == EPI_LN) ? 3 : 1) * PAR_N * 4;
-  // LN: LayerNorm partials per row and column group, x2.  GN variants: [MAXU][8] (mean, rstd) table, then
-  // [MAXU][256] floats of time embedding (GNA) / the LayerNorm partials (GNB)
-  static constexpr int RED_BYTES = (EPI == EPI_LN) ? 2 * GEMM_BM * GEMM_NCG * 8
-                                   : (epi_is_gn(EPI) ? GEMM_GN_MAXU * 8 * 8 + GEMM_GN_MAXU * 256 * 4 : 0);
+  static constexpr int PAR_N = (BN == 128 ? 512 : 1024);  // max N of one launch
+  static constexpr int PAR_BYTES = PAR_N * 4;
+  static constexpr int RED_BYTES = 0;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_BYTES + PAR_BYTES + RED_BYTES + 256;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
 };
@@ -228,7 +197,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // both accumulators of both stages fit (2 x 2 x 128 columns), with 256-wide tiles the dual mode has one stage
   constexpr uint32_t ACC_STRIDE = (epi_has_stats(EPI) && BN == 128) ? 2 * BN : BN;
   constexpr bool DUAL_DOUBLE = (epi_has_stats(EPI) && BN == 128);
-  static_assert(!epi_is_gn(EPI) || BN == 256, "fused GroupNorm epilogues need the whole 256-channel row in one tile");
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "BN must be 128 or 256");
 
@@ -302,11 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int ncols = min(p.n_tiles * BN, PN);
     for (int i = threadIdx.x - 96; i < ncols; i += 32 * GEMM_EPI_WARPS) {
       s_par[i] = p.bias ? p.bias[i] : 0.f;
-      if constexpr (EPI == EPI_LN) { s_par[PN + i] = p.ln_g[i]; s_par[2 * PN + i] = p.ln_b[i]; }
-      if constexpr (EPI == EPI_SNAKE) { s_par[PN + i] = p.sn_a[i]; s_par[2 * PN + i] = p.sn_ib[i]; }
       if constexpr (epi_has_stats(EPI)) if (p.res_chunk0 > 0 && i < 256) s_par[256 + i] = p.res_bias[i];  // the conv's own N is 256
-      if constexpr (epi_is_gn(EPI)) { s_par[512 + i] = p.gn_g[i]; s_par[768 + i] = p.gn_b[i]; }
-      if constexpr (EPI == EPI_GNB) { s_par[1024 + i] = p.ln_g[i]; s_par[1280 + i] = p.ln_b[i]; }
     }
   }
   tc_fence_before();
@@ -389,11 +353,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 
   pdl_wait();  // everything below touches memory the previous kernel may still be using
-  if constexpr (epi_is_gn(EPI)) {  // the previous fused launch (the last user of the other flag array) has completed
-    if (warp >= 3 && p.flags_clear)
-      for (int i = blockIdx.x * (32 * GEMM_EPI_WARPS) + (threadIdx.x - 96); i < p.nflags; i += gridDim.x * 32 * GEMM_EPI_WARPS)
-        p.flags_clear[i] = 0;
-  }
   if (tl && threadIdx.x == 0) { tl[2] = clock64(); tl[9] = (long long)globaltimer_ns(); }
 
   if (warp == 0) {
@@ -589,8 +548,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t sp0 = spar + (n0 + cbase) * 4;  // bias of this warp's first column
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE + cbase;
 
-      if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_LN || EPI == EPI_SNAKE) {
-        const bool has_res = (EPI == EPI_LN) || (EPI == EPI_PLAIN && p.resid != nullptr);
+      if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN) {
+        const bool has_res = (EPI == EPI_PLAIN && p.resid != nullptr);
         const __half* rbase = has_res ? p.resid + (size_t)rw0 * p.ldr + n0 + cbase : nullptr;
         uint4 rr[4];
         if (has_res) epi_resid_issue(rr, lane, rbase, p.ldr, rows_valid);
@@ -606,7 +565,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (p.tl2 && ew == 0 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 2] = clock64();
 
         float gs[(EPI == EPI_STATS) ? 2 * NCH : 1];
-        float lsum = 0.f, lsq = 0.f;
         __half* obase = p.out + (size_t)rw0 * p.ldo + n0 + cbase;
         float vbuf[2][32];  // accumulator chunk c+1 is fetched from TMEM while chunk c is processed
         if (!(p.dbg & 4)) tmem_ld32(taddr, vbuf[0]);
@@ -625,28 +583,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             epi_resid_add(st, lane, rr, v);
             if (c + 1 < NCH) epi_resid_issue(rr, lane, rbase + (c + 1) * 32, p.ldr, rows_valid);
           }
-          if constexpr (EPI == EPI_SNAKE) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 a4 = lds_f4(sp0 + (PN + c * 32 + 4 * j) * 4);
-              const float4 i4 = lds_f4(sp0 + (2 * PN + c * 32 + 4 * j) * 4);
-              float s;
-              s = fast_sin(v[4 * j + 0] * a4.x); v[4 * j + 0] = fmaf(s * s, i4.x, v[4 * j + 0]);
-              s = fast_sin(v[4 * j + 1] * a4.y); v[4 * j + 1] = fmaf(s * s, i4.y, v[4 * j + 1]);
-              s = fast_sin(v[4 * j + 2] * a4.z); v[4 * j + 2] = fmaf(s * s, i4.z, v[4 * j + 2]);
-              s = fast_sin(v[4 * j + 3] * a4.w); v[4 * j + 3] = fmaf(s * s, i4.w, v[4 * j + 3]);
-            }
-          }
           if constexpr (EPI == EPI_STATS) {  // one 32-column chunk == one GroupNorm group
             float a0 = 0.f, b0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { a0 += v[j]; b0 = fmaf(v[j], v[j], b0); }
             gs[2 * c] = a0; gs[2 * c + 1] = b0;
-          }
-          if constexpr (EPI == EPI_LN) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { lsum += v[j]; lsq = fmaf(v[j], v[j], lsq); }
-            tmem_st32(taddr + c * 32, v);
           }
           if constexpr (EPI == EPI_PLAIN) {
 #pragma unroll
@@ -730,279 +671,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
-        if constexpr (EPI == EPI_LN) {
-          // LayerNorm over the full BN-wide row: combine the two column halves through smem
-          const uint32_t red = smem_u32(s_red) + (as ? GEMM_BM * GEMM_NCG * 8 : 0);  // double-buffered by accumulator stage
-          const int trow = q * 32 + lane;
-          sts_f32(red + (trow * GEMM_NCG + hcol) * 8, lsum);
-          sts_f32(red + (trow * GEMM_NCG + hcol) * 8 + 4, lsq);
-          tmem_st_wait();
-          epi_bar_sync();
-          // sum the column groups in a fixed order so every warp of a row sees bit-identical statistics
-          float tsum = 0.f, tsq = 0.f;
-#pragma unroll
-          for (int g = 0; g < GEMM_NCG; ++g) {
-            tsum += lds_f32(red + (trow * GEMM_NCG + g) * 8);
-            tsq += lds_f32(red + (trow * GEMM_NCG + g) * 8 + 4);
-          }
-          const float mean = tsum * (1.f / BN);
-          const float var = fmaxf(tsq * (1.f / BN) - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + 1e-5f);
-          __half* o2 = p.out2 + (size_t)rw0 * p.ldo + n0 + cbase;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 g4 = lds_f4(sp0 + (PN + c * 32 + 4 * j) * 4);
-              const float4 b4 = lds_f4(sp0 + (2 * PN + c * 32 + 4 * j) * 4);
-              v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, g4.x, b4.x);
-              v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, g4.y, b4.y);
-              v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, g4.z, b4.z);
-              v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, g4.w, b4.w);
-            }
-            epi_store_h32(st, lane, v, o2 + c * 32, p.ldo, rows_valid);
-          }
-        }
-      } else if constexpr (epi_is_gn(EPI)) {
-        // ------------------------------------------------------------------------------------------------
-        // conv + GroupNorm (+Mish, mask, time embedding | +residual, LayerNorm1) in one launch; n_tiles == 1
-        // ------------------------------------------------------------------------------------------------
-        const uint32_t gtab = smem_u32(s_red);                  // [MAXU][8] (mean, rstd)
-        const uint32_t gaux = gtab + GEMM_GN_MAXU * 8 * 8;      // GNA: temb [MAXU][256]; GNB: LayerNorm partials [128][NCG]
-        const int myb = row_ok ? p.rowb[row] : -1;              // -1 on guard rows
-        float mrow = 0.f;
-        if (myb >= 0) mrow = p.rowmask[row];
-        const int b_lo = r0 / p.Lp;
-        const int b_hi = min(p.nutt - 1, (min(p.M, r0 + GEMM_BM) - 1) / p.Lp);
-        uint4 rr[4];
-        const __half* rbase = nullptr;
-        if constexpr (EPI == EPI_GNB) {
-          rbase = p.resid + (size_t)rw0 * p.ldr + cbase;
-          epi_resid_issue(rr, lane, rbase, p.ldr, rows_valid);
-        }
-        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
-        __syncwarp();
-        tc_fence_after();
-        if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
-        // ---- pass 1: per-row sums of this warp's 4 groups (one 32-column chunk == one group)
-        float gs[2 * NCH];
-        {
-          float vbuf[2][32];
-          tmem_ld32(taddr, vbuf[0]);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float* v = vbuf[c & 1];
-            tmem_ld_wait();
-            if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
-            float a0 = 0.f, b0 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = lds_f4(sp0 + (c * 32 + 4 * j) * 4);
-              const float x0 = v[4 * j + 0] + b4.x, x1 = v[4 * j + 1] + b4.y, x2 = v[4 * j + 2] + b4.z, x3 = v[4 * j + 3] + b4.w;
-              a0 += x0; b0 = fmaf(x0, x0, b0);
-              a0 += x1; b0 = fmaf(x1, x1, b0);
-              a0 += x2; b0 = fmaf(x2, x2, b0);
-              a0 += x3; b0 = fmaf(x3, x3, b0);
-            }
-            gs[2 * c] = a0; gs[2 * c + 1] = b0;
-          }
-        }
-        {  // deterministic per-(utterance, 32-row block, group) partial sums, as in EPI_STATS
-          const int wb = rw0 >> 5;
-          const int b0 = __shfl_sync(0xffffffffu, myb, 0);
-          if (__all_sync(0xffffffffu, myb == b0)) {
-            if (b0 >= 0) {
-#pragma unroll
-              for (int j = 0; j < 2 * NCH; ++j) {
-                float x = gs[j];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-                gs[j] = x;
-              }
-              if (lane == 0) {
-                float* dst = p.stats_part + ((size_t)b0 * p.S + (wb - ((b0 * p.Lp) >> 5))) * 16 + ((cbase >> 5) << 1);
-#pragma unroll
-                for (int j = 0; j < 2 * NCH; ++j) dst[j] = gs[j];
-              }
-            }
-          } else {
-            const uint32_t sf = st;                 // [32][9] floats
-            const uint32_t sb = st + 32 * 9 * 4;    // [32] ints
-#pragma unroll
-            for (int j = 0; j < 2 * NCH; ++j) sts_f32(sf + (lane * 9 + j) * 4, gs[j]);
-            sts_u32(sb + lane * 4, (uint32_t)myb);
-            __syncwarp();
-            if (lane < 2 * NCH) {
-              int cur = -1;
-              float acc = 0.f;
-              for (int i = 0; i < 32; ++i) {
-                const int bi = (int)lds_u32(sb + i * 4);
-                if (bi != cur) {
-                  if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + ((cbase >> 5) << 1) + lane] = acc;
-                  cur = bi;
-                  acc = 0.f;
-                }
-                acc += lds_f32(sf + (i * 9 + lane) * 4);
-              }
-              if (cur >= 0) p.stats_part[((size_t)cur * p.S + (wb - ((cur * p.Lp) >> 5))) * 16 + ((cbase >> 5) << 1) + lane] = acc;
-            }
-            __syncwarp();
-          }
-        }
-        __threadfence();
-        epi_bar_sync();
-        // ---- publish this row tile, wait for every row tile holding rows of the tile's utterances
-        if (ew == 0) {
-          if (lane == 0) st_release_gpu(p.flags + tile, 1);
-          const int t_lo = (b_lo * p.Lp) >> 7, t_hi = min(m_tiles - 1, ((b_hi + 1) * p.Lp - 1) >> 7);
-          for (int t = t_lo + lane; t <= t_hi; t += 32) spin_wait_flag(p.flags + t);
-          __syncwarp();
-        }
-        // meanwhile: the second accumulator (res_conv) / the time-embedding rows of the tile's utterances
-        if (p.res_chunk0 > 0) {
-          if (lane == 0) mbar_wait(&tfull_bar[1], aphase);   // the res half completes after the conv half (see the MMA warp)
-          __syncwarp();
-          tc_fence_after();
-          __half* rob = p.res_out + (size_t)rw0 * p.ldo + cbase;
-          float vbuf[2][32];
-          tmem_ld32(taddr + BN, vbuf[0]);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float* v = vbuf[c & 1];
-            tmem_ld_wait();
-            if (c + 1 < NCH) tmem_ld32(taddr + BN + (c + 1) * 32, vbuf[(c + 1) & 1]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = lds_f4(spar + (256 + cbase + c * 32 + 4 * j) * 4);
-              v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-            epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
-          }
-        }
-        if constexpr (EPI == EPI_GNA) {
-          for (int i = threadIdx.x - 96; i < (b_hi - b_lo + 1) * 64; i += 32 * GEMM_EPI_WARPS) {
-            const int uu = i >> 6, c4 = (i & 63) * 4;
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.temb) t4 = *reinterpret_cast<const float4*>(p.temb + (size_t)(p.t_off + (b_lo + uu) * p.t_stride) * p.t_ld + c4);
-            sts_f4(gaux + (uu * 256 + c4) * 4, t4);
-          }
-        }
-        epi_bar_sync();
-        // ---- GroupNorm statistics of the tile's utterances: 4 threads per (utterance, group), fixed order, in double
-        {
-          const int et = threadIdx.x - 96;
-          const int pair = et >> 2, k = et & 3, uu = pair >> 3, g = pair & 7;
-          const int b = b_lo + uu;
-          double s = 0.0, ss = 0.0;
-          if (b <= b_hi) {
-            const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
-            for (int sl = k; sl <= last - first; sl += 4) {
-              const float2 pp = __ldcg(reinterpret_cast<const float2*>(p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * g));
-              s += (double)pp.x;
-              ss += (double)pp.y;
-            }
-          }
-          s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-          if (k == 0 && b <= b_hi) {
-            const double n = 32.0 * (double)p.L;
-            const double mean = s / n;
-            double var = ss / n - mean * mean;
-            if (var < 0.0) var = 0.0;
-            sts_f32(gtab + pair * 8, (float)mean);
-            sts_f32(gtab + pair * 8 + 4, (float)(1.0 / sqrt(var + 1e-5)));
-          }
-        }
-        epi_bar_sync();
-        if (tl && ew == 0 && lane == 0 && ti == 0) tl[11] = clock64();
-        // ---- pass 2: normalise the accumulator still held in TMEM
-        const int uu = (myb >= 0) ? myb - b_lo : 0;
-        __half* obase = p.out + (size_t)rw0 * p.ldo + cbase;
-        float lsum = 0.f, lsq = 0.f;
-        {
-          float vbuf[2][32];
-          tmem_ld32(taddr, vbuf[0]);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float* v = vbuf[c & 1];
-            tmem_ld_wait();
-            if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
-            const float2 mr = lds_f2(gtab + (uu * 8 + (cbase >> 5) + c) * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = cbase + c * 32 + 4 * j;
-              const float4 b4 = lds_f4(spar + col * 4);
-              const float4 g4 = lds_f4(spar + (512 + col) * 4);
-              const float4 e4 = lds_f4(spar + (768 + col) * 4);
-              float x0 = fmaf((v[4 * j + 0] + b4.x - mr.x) * mr.y, g4.x, e4.x);
-              float x1 = fmaf((v[4 * j + 1] + b4.y - mr.x) * mr.y, g4.y, e4.y);
-              float x2 = fmaf((v[4 * j + 2] + b4.z - mr.x) * mr.y, g4.z, e4.z);
-              float x3 = fmaf((v[4 * j + 3] + b4.w - mr.x) * mr.y, g4.w, e4.w);
-              x0 = mish_f(x0) * mrow; x1 = mish_f(x1) * mrow; x2 = mish_f(x2) * mrow; x3 = mish_f(x3) * mrow;
-              if constexpr (EPI == EPI_GNA) {
-                const float4 t4 = lds_f4(gaux + (uu * 256 + col) * 4);
-                x0 = (x0 + t4.x) * mrow; x1 = (x1 + t4.y) * mrow; x2 = (x2 + t4.z) * mrow; x3 = (x3 + t4.w) * mrow;
-              }
-              const bool ok = myb >= 0;   // guard rows stay zero (they are the convs' zero padding)
-              v[4 * j + 0] = ok ? x0 : 0.f; v[4 * j + 1] = ok ? x1 : 0.f; v[4 * j + 2] = ok ? x2 : 0.f; v[4 * j + 3] = ok ? x3 : 0.f;
-            }
-            if constexpr (EPI == EPI_GNB) {
-              epi_resid_add(st, lane, rr, v);
-              if (c + 1 < NCH) epi_resid_issue(rr, lane, rbase + (c + 1) * 32, p.ldr, rows_valid);
-              if (myb < 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { lsum += v[j]; lsq = fmaf(v[j], v[j], lsq); }
-              tmem_st32(taddr + c * 32, v);
-            }
-            epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid);
-          }
-        }
-        if constexpr (EPI == EPI_GNB) {
-          // LayerNorm1 over the 256-wide row: combine the two column halves through smem
-          const int trow = q * 32 + lane;
-          sts_f32(gaux + (trow * GEMM_NCG + hcol) * 8, lsum);
-          sts_f32(gaux + (trow * GEMM_NCG + hcol) * 8 + 4, lsq);
-          tmem_st_wait();
-          epi_bar_sync();
-          float tsum = 0.f, tsq = 0.f;
-#pragma unroll
-          for (int g = 0; g < GEMM_NCG; ++g) {
-            tsum += lds_f32(gaux + (trow * GEMM_NCG + g) * 8);
-            tsq += lds_f32(gaux + (trow * GEMM_NCG + g) * 8 + 4);
-          }
-          const float mean = tsum * (1.f / 256.f);
-          const float rstd = rsqrtf(fmaxf(tsq * (1.f / 256.f) - mean * mean, 0.f) + 1e-5f);
-          __half* o2 = p.out2 + (size_t)rw0 * p.ldo + cbase;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = cbase + c * 32 + 4 * j;
-              const float4 g4 = lds_f4(spar + (1024 + col) * 4);
-              const float4 b4 = lds_f4(spar + (1280 + col) * 4);
-              v[4 * j + 0] = (myb >= 0) ? fmaf((v[4 * j + 0] - mean) * rstd, g4.x, b4.x) : 0.f;
-              v[4 * j + 1] = (myb >= 0) ? fmaf((v[4 * j + 1] - mean) * rstd, g4.y, b4.y) : 0.f;
-              v[4 * j + 2] = (myb >= 0) ? fmaf((v[4 * j + 2] - mean) * rstd, g4.z, b4.z) : 0.f;
-              v[4 * j + 3] = (myb >= 0) ? fmaf((v[4 * j + 3] - mean) * rstd, g4.w, b4.w) : 0.f;
-            }
-            epi_store_h32(st, lane, v, o2 + c * 32, p.ldo, rows_valid);
-          }
-        }
       } else if constexpr (EPI == EPI_QKV) {
         if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
-        if (n_tile < 2 || p.v != nullptr) {
+        {
           __half* dst = (n_tile == 0 ? p.q : (n_tile == 1 ? p.k : p.v)) + (size_t)rw0 * BN + cbase;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -1010,22 +684,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
             epi_store_h32(st, lane, v, dst + c * 32, BN, rows_valid);
-          }
-        } else {
-          const int b = row_ok ? p.rowb[row] : -1;
-          const int t = row - b * p.Lp;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-            if (b >= 0) {
-              // tile column cc = cbase + c*32 + j -> head cc/64, dim cc%64 ; lanes = consecutive frames
-              const int cc = cbase + c * 32;
-              __half* dst = p.vt + ((size_t)(b * 2 + (cc >> 6)) * 64 + (cc & 63)) * p.Lpad + t;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dst[(size_t)j * p.Lpad] = __float2half_rn(v[j]);
-            }
           }
         }
       } else {  // EPI_FINAL
@@ -1077,12 +735,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       __syncwarp();
       const bool dual_split = !DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0;
       if (lane == 0) {
-        // dual_split: EPI_STATS released the conv half above and releases the res half here; the fused-GroupNorm
-        // epilogues hold both halves to the end
-        if (dual_split && epi_is_gn(EPI)) {
-          if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[0]), 0));
-          else mbar_arrive(&tempty_bar[0]);
-        }
+        // dual_split: EPI_STATS released the conv half above and releases the res half here
         uint64_t* eb = &tempty_bar[dual_split ? 1 : as];
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(eb), 0));   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(eb);

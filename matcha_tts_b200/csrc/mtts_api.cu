@@ -14,13 +14,10 @@
 #include <vector>
 
 #include "../../include/mtts.h"
-#include "attention.cuh"
-#include "attention2.cuh"
 #include "attention3.cuh"
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
 #include "gemm_tc.cuh"
-#include "ln_qkv.cuh"
 
 using namespace mtts;
 
@@ -38,6 +35,28 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                     \
       return fail(MTTS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
   } while (0)
+
+// Every C entry point that touches CUDA runs with the handle's device current and restores the caller's device on
+// return: kernels, side streams, events and cudaFuncSetAttribute all bind to the CURRENT device, and the caller (e.g.
+// torch with tensors on cuda:1 while cuda:0 is current) must not see its current device change.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
+    if (cur != dev) {
+      if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
+      prev = cur;
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(h)                                                                        \
+  DeviceGuard _dg((h)->device);                                                                \
+  if (!_dg.ok) return fail(MTTS_ECUDA, "cannot make device " + std::to_string((h)->device) + " current")
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps (driver entry point fetched at run time: the .so has no link-time libcuda dependency)
@@ -146,19 +165,17 @@ struct StageW {
 };
 
 struct WsLayout {
-  int B, T, H, LpT, LpH, rowsT, rowsH, LpadT, LpadH, S, cinp, nt_max;
+  int B, T, H, LpT, LpH, rowsT, rowsH, S, cinp, nt_max;
   size_t maskT, maskH, rowbT, rowbH, npadT, npadH, tvals, te_e, te_h1, te_h2, te6, part;
-  size_t x0, y, res, h1, xr, a, xa, q, k, o, vt, v, s;
+  size_t x0, y, res, h1, xr, a, q, k, o, v;
   size_t skip0, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF, zmid;
-  size_t flags;   // two arrays of nflags ints: inter-CTA flags of the fused GroupNorm conv launches (ping-pong)
-  int nflags;
-  size_t vt_bytes, total;
+  size_t total;
 };
 
 struct LevelMaps {
   TMap h1, a;
-  CUtensorMap o, s, q, k, vt;
-  CUtensorMap k2, v2;  // attention2.cuh: k / v [rows][128] with KT-row boxes
+  CUtensorMap q;
+  CUtensorMap k2, v2;  // k / v [rows][128] with KT-row boxes
   int KT, nkv;         // keys per tile (multiple of 16, <= 192) and tiles per utterance
   CUtensorMap o3;  // o as [2][rows][64], box {64, 128, 2} (fused tail)
 };
@@ -166,8 +183,6 @@ struct Plan {
   WsLayout w;
   char* ws;
   int te_n = -1, te_solver = -1;  // the solver's time-embedding table in ws.te6 is valid for (n_timesteps, solver)
-  int flag_par = 0;     // which flag array the next fused GroupNorm launch uses
-  int grid_cap = 0;     // CTAs one flag-synchronised launch of this plan may use (#SMs / chains: all must be co-resident)
   LevelMaps lv[2];
   TMap x0, skip0, skip0_pair, xD0, skip1, xD1, xM0, xM1, xU0s, xU0, xU1s, xF;
 };
@@ -197,22 +212,13 @@ struct MttsHandle {
   bool maps_ready = false;
   std::map<std::tuple<const void*, int, int>, Plan> plans;
   std::map<GraphKey, std::pair<cudaGraphExec_t, int>> graphs;
+  std::map<const void*, int> ws_nsub;   // chain partition last laid over each solver workspace
   int launch_count = 0, launch_limit = -1;
-  int conv_bn = 256;       // MTTS_BN: N tile of the conv GEMMs at level T (256, or 128: twice the CTAs / half the tile)
-  int conv_bn_h = 256;     // MTTS_BN_H: same at level T/2 (87 row tiles at B=64, T=344)
-  bool a_prefetch = true;  // MTTS_NO_APREFETCH=1: no early L2 prefetch of the first activation tiles
-  bool w_hint = true;      // MTTS_NO_WHINT=1: load weights without the L2 evict_last hint
-  bool fused_lnqkv = false; // MTTS_LNQKV=1: ln_qkv_kernel instead of the GroupNorm-apply+LayerNorm1 launch followed by the QKV GEMM (measured slower)
-  bool fused_gn = false;   // MTTS_GNFUSE=1: GroupNorm-apply inside the conv launches (EPI_GNA / EPI_GNB, inter-CTA flags) instead of
-                           // separate launches.  Parity-green but slower (8.49 vs 6.97 ms/solve at one chain): profiles/r01_chain_sweep.txt
-  int gn_rpw = 4;           // MTTS_GN_RPW=8: GroupNorm-apply with 8 rows per warp in flight (32 rows per block) instead of 4
-  bool tap3_plain = true, tap3_res = true;   // MTTS_TAP3=1: only the convs without res_conv, =2: only those with (A/B measurements)
+  bool a_prefetch = true;  // early L2 prefetch of the first activation tiles
+  bool w_hint = true;      // weights are loaded with the L2 evict_last hint
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
-  bool fused_tail = true;  // MTTS_NO_TAIL=1: run to_out / FF1 / FF2 as three GEMM launches instead of ff_tail_kernel
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
-  bool attn_v3 = true;   // MTTS_ATTN_V2=1: second-generation attention kernel (one thread per query row); default: attention3 (two threads per row)
-  bool attn_v2 = true;   // MTTS_ATTN_V1=1: first-generation attention kernel (128-key tiles, V transposed by the QKV epilogue)
   int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
   bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
                           // pair launches measured -1% (4.57 vs 4.63 M frames/s) although the kernel alone gains 5-10% at full occupancy
@@ -223,13 +229,6 @@ struct MttsHandle {
   // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
   // every kernel of a chain is small (tens of tiles) and latency-bound on its own
   int nsub_override = 0;  // MTTS_NSUB in the environment; 0 = heuristic
-  // staggered chains (MTTS_STAGGER=1; off: measured slower, 7.03 vs 6.61 ms -- a chain's step time barely depends on
-  // its batch, so serialising the level-T blocks serialises the solve): the level-T parts of the chains' estimator
-  // evaluations take turns (cross-chain events), one chain at level T/2 while the other is at level T
-  bool stagger = false;
-  int gn_cap = 0;          // grid cap of the flag-synchronised launches being enqueued (set per plan)
-  mutable bool pdl_break = false;  // next launch follows a cross-chain event wait: plain (non-programmatic) launch
-  std::vector<cudaEvent_t> ev_turn;
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> ev_join;
   cudaEvent_t ev_fork = nullptr;
@@ -400,12 +399,15 @@ static int build_weight_maps(MttsHandle* h) {
 static const int kMaxTimes = 2048;  // rows of the time-embedding table (>= B and >= 2*n_timesteps)
 
 static bool ws_layout(const MttsHandle* h, int B, int T, WsLayout* w) {
-  if (B < 1 || T < 2 || (T & 1) || B > kMaxTimes) return false;
+  if (B < 1 || T < 1 || B > kMaxTimes) return false;
   memset(w, 0, sizeof *w);
   const int C = h->cfg.channels, NF = h->cfg.out_channels;
-  w->B = B; w->T = T; w->H = T / 2; w->LpT = T + 2; w->LpH = T / 2 + 1;
+  // Level T/2 holds H = ceil(T/2) frames (stride-2 conv, k3 p1: reference model.py:797; mask[:, :, ::2] :1003).  The stride-2
+  // conv and the ConvTranspose read / write level T through a row-pair view, so rows per utterance are even at level T:
+  // two guard rows for even T, three for odd T -- the ConvTranspose's surplus frame 2H-1 = T of an odd T lands on a
+  // guard row and is masked to zero, which is the reference's F.interpolate(nearest) crop (model.py:1027-1028).
+  w->B = B; w->T = T; w->H = (T + 1) / 2; w->LpT = T + 2 + (T & 1); w->LpH = w->LpT / 2;
   w->rowsT = B * w->LpT; w->rowsH = B * w->LpH;
-  w->LpadT = (int)align_up(T, 8); w->LpadH = (int)align_up(T / 2, 8);
   w->S = (T + 31) / 32 + 1;
   w->cinp = h->cinp; w->nt_max = kMaxTimes;
   size_t cur = 0;
@@ -419,18 +421,13 @@ static bool ws_layout(const MttsHandle* h, int B, int T, WsLayout* w) {
   w->part = alloc(4ull * B * w->S * 16);
   w->x0 = alloc(2 * rT * w->cinp);
   w->y = alloc(2 * rT * C); w->res = alloc(2 * rT * C); w->h1 = alloc(2 * rT * C); w->xr = alloc(2 * rT * C);
-  w->a = alloc(2 * rT * C); w->xa = alloc(2 * rT * C);
+  w->a = alloc(2 * rT * C);
   w->q = alloc(2 * rT * 128); w->k = alloc(2 * rT * 128); w->o = alloc(2 * rT * 128);
-  w->vt_bytes = 2ull * B * 128 * w->LpadT;
-  w->vt = alloc(w->vt_bytes);
   w->v = alloc(2 * rT * 128);
-  w->s = alloc(2 * rT * 4 * C);
   w->skip0 = alloc(2 * rT * C); w->xD0 = alloc(2 * rH * C); w->skip1 = alloc(2 * rH * C); w->xD1 = alloc(2 * rH * C);
   w->xM0 = alloc(2 * rH * C); w->xM1 = alloc(2 * rH * C); w->xU0s = alloc(2 * rH * C);
   w->xU0 = alloc(2 * rT * C); w->xU1s = alloc(2 * rT * C); w->xF = alloc(2 * rT * C);
   w->zmid = alloc(4ull * B * NF * T);
-  w->nflags = (int)align_up((rT + 127) / 128 + 1, 32);
-  w->flags = alloc(2ull * 4 * w->nflags);
   w->total = cur;
   return true;
 }
@@ -440,7 +437,7 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
   auto it = h->plans.find(key);
   if (it != h->plans.end()) { *out = &it->second; return 0; }
   Plan P;
-  if (!ws_layout(h, B, T, &P.w)) return fail(MTTS_EINVAL, "unsupported shape: need B >= 1, T even and >= 2");
+  if (!ws_layout(h, B, T, &P.w)) return fail(MTTS_EINVAL, "unsupported shape: need 1 <= B <= 2048 and T >= 1");
   if (ws_bytes < P.w.total) return fail(MTTS_ENOMEM, "workspace too small (see mtts_workspace_bytes)");
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(MTTS_EINVAL, "workspace must be 1024-byte aligned");
   if (int e = init_encode()) return e;
@@ -450,16 +447,11 @@ static int get_plan(MttsHandle* h, void* ws, size_t ws_bytes, int B, int T, cuda
   char* b = P.ws;
   for (int lv = 0; lv < 2; ++lv) {
     const uint64_t rows = lv ? w.rowsH : w.rowsT;
-    const int Lpad = lv ? w.LpadH : w.LpadT;
     LevelMaps& m = P.lv[lv];
     if (make_tmap(&m.h1, b + w.h1, rows, C, C, 128)) return MTTS_ECUDA;
     if (make_tmap(&m.a, b + w.a, rows, C, C, 128)) return MTTS_ECUDA;
-    if (make_map(&m.o, b + w.o, rows, 128, 128, 128)) return MTTS_ECUDA;
     if (make_map3(&m.o3, b + w.o, rows, 2, 128, 128)) return MTTS_ECUDA;
-    if (make_map(&m.s, b + w.s, rows, 4 * C, 4 * C, 128)) return MTTS_ECUDA;
     if (make_map(&m.q, b + w.q, rows, 128, 128, 128)) return MTTS_ECUDA;
-    if (make_map(&m.k, b + w.k, rows, 128, 128, 128)) return MTTS_ECUDA;
-    if (make_map(&m.vt, b + w.vt, (uint64_t)B * 128, Lpad, Lpad, 64)) return MTTS_ECUDA;
     const int L = lv ? w.H : w.T;
     m.nkv = (L + ATT2_KT_MAX - 1) / ATT2_KT_MAX;
     m.KT = (int)align_up((L + m.nkv - 1) / m.nkv, 16);
@@ -522,8 +514,7 @@ static cudaError_t launch_k(const MttsHandle* h, void (*kern)(KArgs...), dim3 gr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (h->use_pdl && !h->profiling && !h->pdl_break) ? 1 : 0;
-  h->pdl_break = false;
+  cfg.numAttrs = (h->use_pdl && !h->profiling) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -539,8 +530,7 @@ static cudaError_t launch_k_pair(const MttsHandle* h, void (*kern)(KArgs...), di
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (h->use_pdl && !h->profiling && !h->pdl_break) ? 2 : 1;
-  h->pdl_break = false;
+  cfg.numAttrs = (h->use_pdl && !h->profiling) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -565,7 +555,6 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = p.m_major ? m_tiles : m_tiles * p.n_tiles;   // m_major: one CTA per row tile, all its N tiles
   int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  if (epi_is_gn(EPI) && h->gn_cap > 0 && grid > h->gn_cap) grid = h->gn_cap;
   GemmParams pp = p;
   pp.tl = nullptr;
   pp.tl2 = h->tl2_buf;
@@ -612,7 +601,7 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
       if (h->tap3) {
         const int nsrc = (p.num_segs == 3 || p.num_segs == 4) ? 1 : ((p.num_segs == 6 || p.num_segs == 8) ? 2 : 0);
         const bool has_res = nsrc && p.num_segs == 4 * nsrc;
-        bool ok = nsrc > 0 && (has_res || h->tap3_plain);
+        bool ok = nsrc > 0;
         int CH = 0;
         for (int s = 0; ok && s < nsrc; ++s) CH += p.seg[s].nchunks;
         for (int t = 0; ok && t < (has_res ? 4 : 3); ++t)
@@ -620,7 +609,7 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
             const GemmSeg& g = p.seg[t * nsrc + s];
             ok = g.src == s && g.row_shift == (t < 3 ? t - 1 : 0) && g.col0 == p.seg[s].col0 && g.nchunks == p.seg[s].nchunks;
           }
-        ok = ok && p.res_chunk0 == (has_res ? 3 * CH : 0) && (!has_res || h->tap3_res);
+        ok = ok && p.res_chunk0 == (has_res ? 3 * CH : 0);
         if (ok) {
           GemmParams q = p;
           q.tap3 = nsrc;
@@ -643,38 +632,11 @@ static const int kTaps3[3] = {-1, 0, 1};
 static const int kTap1[1] = {0};
 
 struct LevelCtx {
-  int lv, L, Lp, rows, Lpad;
+  int lv, L, Lp, rows;
   const float* mask;
   const int* rowb;
   const int* npad;
 };
-
-// The GroupNorm that follows a conv can be finished inside the conv launch (EPI_GNA / EPI_GNB) when a 128-row tile
-// touches at most GEMM_GN_MAXU utterances and the flag waits cannot form a cycle: every wait set (the row tiles of a
-// tile's utterances) is shorter than half the grid, or the launch has one tile per CTA.
-static bool gn_fusable(const MttsHandle* h, const Plan& P, const LevelCtx& lc) {
-  if (!h->fused_gn) return false;
-  const int maxu = 127 / lc.Lp + 2;
-  if (maxu > GEMM_GN_MAXU) return false;
-  const int tiles = (lc.rows + 127) / 128;
-  const int cap = P.grid_cap > 0 ? P.grid_cap : h->num_sms;
-  const int span = (maxu * lc.Lp + 127) / 128 + 1;
-  return tiles <= cap || 2 * span <= cap;
-}
-static void gn_fill(MttsHandle* h, Plan& P, const LevelCtx& lc, GemmParams& p, size_t gamma, size_t beta) {
-  const WsLayout& w = P.w;
-  int* fl = reinterpret_cast<int*>(P.ws + w.flags);
-  p.flags = fl + P.flag_par * w.nflags;
-  p.flags_clear = fl + (P.flag_par ^ 1) * w.nflags;
-  p.nflags = w.nflags;
-  P.flag_par ^= 1;
-  p.L = lc.L; p.nutt = w.B;
-  p.gn_g = reinterpret_cast<const float*>(h->arena + gamma);
-  p.gn_b = reinterpret_cast<const float*>(h->arena + beta);
-  p.rowmask = lc.mask; p.mask_mul = 1; p.mask_nstep = 0;
-  p.n_tiles = 1;
-  h->gn_cap = P.grid_cap > 0 ? P.grid_cap : h->num_sms;
-}
 
 // One resnet + transformer stage (reference ResnetBlock1D :785-790 + BasicTransformerBlock :733-744).
 static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TMap& in0, const TMap& in1,
@@ -690,8 +652,6 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
   float* part = reinterpret_cast<float*>(ws + w.part);
   const float* te6 = reinterpret_cast<const float*>(ws + w.te6);
 
-  const int conv_bn = lc.lv ? h->conv_bn_h : h->conv_bn;
-  const bool fuse_gn = gn_fusable(h, P, lc);
   const double fr = 2.0 * w.B * (double)lc.L;   // algorithmic FLOPs = fr * N * K (valid rows, unpadded K/N)
   const int ci_real = (s == 0) ? h->cfg.in_channels : sw.src_cols[0] + sw.src_cols[1];
   GemmParams base{};
@@ -709,134 +669,68 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (sw.src_cols[1]) p.seg[p.num_segs++] = GemmSeg{1, 0, 0, sw.src_cols[1] / 64};
     p.res_chunk0 = conv_chunks; p.res_bias = F(sw.res_b); p.res_out = H(w.res);
     p.bias = F(sw.c1_b); p.out = H(w.y);
-    if (fuse_gn) {   // ... and h1 = (Mish(GN(y))*m + temb)*m in the same launch
-      gn_fill(h, P, lc, p, sw.gn1_g, sw.gn1_b);
-      p.temb = te6 + (size_t)s * C; p.t_off = t_off; p.t_stride = t_stride; p.t_ld = 6 * C; p.out = H(w.h1);
-      if (int e = launch_gemm<256, EPI_GNA>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
-    }
-    else if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
-    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e; }
+    p.n_tiles = 1;
+    if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
   }
-  const int gn_rows = 4 * h->gn_rpw;
-  const dim3 gn_grid((lc.Lp + gn_rows - 1) / gn_rows, w.B);
+  const dim3 gn_grid((lc.Lp + GN_ROWS - 1) / GN_ROWS, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
-  if (!fuse_gn) {
+  {
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : h->gn_rpw == 2 ? gn_apply_kernel<0, 2> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
     GemmParams p = base;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(sw.c2_b); p.out = H(w.y);
-    if (fuse_gn) {   // ... and x_r = Mish(GN(y))*m + res ; a = LN1(x_r) in the same launch
-      gn_fill(h, P, lc, p, sw.gn2_g, sw.gn2_b);
-      p.resid = H(w.res); p.ln_g = F(sw.ln1_g); p.ln_b = F(sw.ln1_b); p.out = H(w.xr); p.out2 = H(w.a);
-      if (int e = launch_gemm<256, EPI_GNB>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
-    }
-    else if (conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
-    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e; }
+    p.n_tiles = 1;
+    if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
   }
-  if (fuse_gn) {
-    // q | k | v^T
+  // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
+  {
+    GnParams g{};
+    g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
+    g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
+    g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+  }
+  // q | k | v
+  {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
-    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.v = h->attn_v2 ? H(w.v) : nullptr; p.Lpad = lc.Lpad;
+    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.v = H(w.v);
     if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
-  } else if (h->fused_lnqkv && h->fused_tail) {
-    // x_r = Mish(GN(y))*m + res ; a = LN1(x_r) (on chip) ; q | k | v^T = a Wqkv^T   -- one kernel
-    if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
-      LnQkvParams lp{};
-      lp.M = lc.rows; lp.L = lc.L; lp.Lp = lc.Lp; lp.S = w.S;
-      lp.y = H(w.y); lp.res = H(w.res); lp.stats_part = part;
-      lp.gamma = F(sw.gn2_g); lp.beta = F(sw.gn2_b); lp.ln_g = F(sw.ln1_g); lp.ln_b = F(sw.ln1_b);
-      lp.rowmask = lc.mask; lp.rowb = lc.rowb; lp.xr = H(w.xr);
-      lp.q = H(w.q); lp.k = H(w.k); lp.vt = H(w.vt); lp.v = h->attn_v2 ? H(w.v) : nullptr; lp.Lpad = lc.Lpad; lp.w_hint = h->w_hint ? 1 : 0;
-      const int tiles = (lc.rows + 127) / 128;
-      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-      CUDA_TRY(launch_k(h, ln_qkv_kernel, dim3(grid), dim3(LQ_THREADS), LQ_SMEM, stream, sw.m_qkv.d3, lp));
-      launched(h);
-    }
-  } else {
-    // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
-    {
-      GnParams g{};
-      g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
-      g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
-      g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-      if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<1, 8> : h->gn_rpw == 2 ? gn_apply_kernel<1, 2> : gn_apply_kernel<1, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
-    }
-    // q | k | v^T
-    {
-      GemmParams p = base;
-      segs_taps(p, 1, kTap1, C, 0);
-      p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.vt = H(w.vt); p.v = h->attn_v2 ? H(w.v) : nullptr; p.Lpad = lc.Lpad;
-      if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
-    }
   }
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
     dim3 grid((lc.L + 127) / 128, 2, w.B);
-    if (h->attn_v2) {
-      Attn2Params ap{};
-      ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
-      ap.v = H(w.v); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
-      if (h->attn_v3) CUDA_TRY(launch_k(h, attention3_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
-      else CUDA_TRY(launch_k(h, attention2_kernel, grid, dim3(ATT2_THREADS), ATT2_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
-    } else {
-      AttnParams ap{};
-      ap.L = lc.L; ap.Lp = lc.Lp; ap.Lpad = lc.Lpad; ap.rowmask = lc.mask; ap.npad = lc.npad;
-      ap.vt = H(w.vt); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
-      CUDA_TRY(launch_k(h, attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, lm.q, lm.k, lm.vt, ap));
-    }
+    Attn2Params ap{};
+    ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
+    ap.v = H(w.v); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
+    CUDA_TRY(launch_k(h, attention3_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
     launched(h);
   }
-  if (h->fused_tail) {
-    // x_a = x_r + o Wo^T + b_o ; c = LN3(x_a) ; out = (x_a + SnakeBeta(c W1^T + b1) W2^T + b2) * m   -- one kernel
-    if (can_launch(h, MTTS_KIND_GEMM, fr * C * 128 + 2.0 * fr * 4 * C * C)) {
-      TailParams tp{};
-      tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
-      tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
-      tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
-      tp.tl = h->tail_tl;
-      const int tiles = (lc.rows + 127) / 128;
-      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-      if (h->tail_pairs) {
-        const int units = (tiles + 1) / 2;
-        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
-        CUDA_TRY(launch_k_pair(h, ff_tail_kernel<2>, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
-                               sw.m_ff2_h, tp));
-      } else {
-        CUDA_TRY(launch_k(h, ff_tail_kernel<1>, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
-      }
-      launched(h);
+  // x_a = x_r + o Wo^T + b_o ; c = LN3(x_a) ; out = (x_a + SnakeBeta(c W1^T + b1) W2^T + b2) * m   -- one kernel
+  if (can_launch(h, MTTS_KIND_GEMM, fr * C * 128 + 2.0 * fr * 4 * C * C)) {
+    TailParams tp{};
+    tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
+    tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
+    tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
+    tp.tl = h->tail_tl;
+    const int tiles = (lc.rows + 127) / 128;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    if (h->tail_pairs) {
+      const int units = (tiles + 1) / 2;
+      const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+      CUDA_TRY(launch_k_pair(h, ff_tail_kernel<2>, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
+                             sw.m_ff2_h, tp));
+    } else {
+      CUDA_TRY(launch_k(h, ff_tail_kernel<1>, dim3(grid), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo, sw.t_ff1, sw.m_ff2, tp));
     }
-    return 0;
-  }
-  // x_a = x_r + o Wo^T + b ; c = LN3(x_a)
-  {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, 128, 0);
-    p.n_tiles = 1; p.bias = F(sw.o_b); p.resid = H(w.xr); p.out = H(w.xa);
-    p.ln_g = F(sw.ln3_g); p.ln_b = F(sw.ln3_b); p.out2 = H(w.a);
-    if (int e = launch_gemm_maps<256, EPI_LN, 1>(h, lm.o, lm.o, sw.m_wo, p, stream, fr * C * 128)) return e;
-  }
-  // s = SnakeBeta(c W1^T + b1)
-  {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, C, 0);
-    p.n_tiles = 4; p.bias = F(sw.ff1_b); p.sn_a = F(sw.sn_a); p.sn_ib = F(sw.sn_ib); p.out = H(w.s); p.ldo = 4 * C;
-    if (int e = launch_gemm_maps<256, EPI_SNAKE, 1>(h, lm.a.d2, lm.a.d2, sw.m_ff1, p, stream, fr * 4 * C * C)) return e;
-  }
-  // out = (x_a + s W2^T + b2) * m      (every consumer of a stage output masks it first)
-  {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, 4 * C, 0);
-    p.n_tiles = 1; p.bias = F(sw.ff2_b); p.resid = H(w.xa); p.rowmask = lc.mask; p.out = out;
-    if (int e = launch_gemm_maps<256, EPI_PLAIN, 1>(h, lm.s, lm.s, sw.m_ff2, p, stream, fr * C * 4 * C)) return e;
+    launched(h);
   }
   return 0;
 }
@@ -844,21 +738,17 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
 // One estimator evaluation on the operand buffer X0 (z | mu | spks already staged, masked).
 // Writes zout = (zbase ? zbase + zscale * v : v) in (B, 80, T) fp32 and, if upd_x0, refreshes the
 // z channels of X0 with zout * mask for the next evaluation.
-// `parts` selects which section is enqueued (the staggered chain schedule interleaves them across chains):
-// EST_HEAD = stage 0 at level T, EST_HALF = everything at level T/2 (down conv .. up ConvTranspose),
-// EST_TAIL = stage 5, last level conv, final block, projection + ODE update.
-enum { EST_HEAD = 1, EST_HALF = 2, EST_TAIL = 4, EST_ALL = 7 };
 static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float* zout, const float* zbase, float zscale,
-                         bool upd_x0, cudaStream_t stream, int parts = EST_ALL) {
+                         bool upd_x0, cudaStream_t stream) {
   const WsLayout& w = P.w;
   char* ws = P.ws;
   const char* ar = h->arena;
   const int C = h->cfg.channels;
   auto H = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
   auto F = [&](size_t off) { return reinterpret_cast<const float*>(ar + off); };
-  LevelCtx lT{0, w.T, w.LpT, w.rowsT, w.LpadT, reinterpret_cast<const float*>(ws + w.maskT),
+  LevelCtx lT{0, w.T, w.LpT, w.rowsT, reinterpret_cast<const float*>(ws + w.maskT),
               reinterpret_cast<const int*>(ws + w.rowbT), reinterpret_cast<const int*>(ws + w.npadT)};
-  LevelCtx lH{1, w.H, w.LpH, w.rowsH, w.LpadH, reinterpret_cast<const float*>(ws + w.maskH),
+  LevelCtx lH{1, w.H, w.LpH, w.rowsH, reinterpret_cast<const float*>(ws + w.maskH),
               reinterpret_cast<const int*>(ws + w.rowbH), reinterpret_cast<const int*>(ws + w.npadH)};
   float* part = reinterpret_cast<float*>(ws + w.part);
 
@@ -880,27 +770,24 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     }
     // k3 convs: out rows * 256 * 768; ConvTranspose: B*H input rows * 512 outputs * 512 (two 2-tap phases)
     const double af = (mode == 2) ? 2.0 * w.B * (double)w.H * 512 * 512 : 2.0 * w.B * (double)lc.L * C * 3 * C;
-    if ((p.M == lH.rows ? h->conv_bn_h : h->conv_bn) == 128) { p.n_tiles *= 2; p.m_major = 1; return launch_gemm<128, EPI_PLAIN>(h, in, in, wmap, p, stream, af); }
     return launch_gemm<256, EPI_PLAIN>(h, in, in, wmap, p, stream, af);
   };
 
   // down 0 @T
-  if (parts & EST_HEAD)
-    if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
-  if (parts & EST_HALF) {
-    if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
-    // down 1 @T/2
-    if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
-    if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
-    // mid
-    if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
-    if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
-    // up 0 @T/2 : cat[x, skip1]
-    if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
+  if (int e = run_stage(h, P, 0, lT, P.x0, P.x0, H(w.skip0), t_off, t_stride, stream)) return e;
+  if (int e = level_conv(P.skip0_pair, h->m_down0, h->b_down0, lH, H(w.xD0), 1)) return e;
+  // down 1 @T/2
+  if (int e = run_stage(h, P, 1, lH, P.xD0, P.xD0, H(w.skip1), t_off, t_stride, stream)) return e;
+  if (int e = level_conv(P.skip1, h->m_down1, h->b_down1, lH, H(w.xD1), 0)) return e;
+  // mid
+  if (int e = run_stage(h, P, 2, lH, P.xD1, P.xD1, H(w.xM0), t_off, t_stride, stream)) return e;
+  if (int e = run_stage(h, P, 3, lH, P.xM0, P.xM0, H(w.xM1), t_off, t_stride, stream)) return e;
+  // up 0 @T/2 : cat[x, skip1]
+  if (int e = run_stage(h, P, 4, lH, P.xM1, P.skip1, H(w.xU0s), t_off, t_stride, stream)) return e;
+  {
     LevelCtx lc = lT;  // mask of the OUTPUT rows (level T), indexed 2*r + phase
     if (int e = level_conv(P.xU0s, h->m_up0, h->b_up0, lc, H(w.xU0), 2)) return e;
   }
-  if (!(parts & EST_TAIL)) return 0;
   // up 1 @T : cat[x, skip0]
   if (int e = run_stage(h, P, 5, lT, P.xU0, P.skip0, H(w.xU1s), t_off, t_stride, stream)) return e;
   if (int e = level_conv(P.xU1s, h->m_up1, h->b_up1, lT, H(w.xF), 0)) return e;
@@ -910,20 +797,13 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     p.M = lT.rows; p.rowb = lT.rowb; p.Lp = lT.Lp; p.stats_part = part; p.S = w.S; p.ldo = C; p.ldr = C;
     segs_taps(p, 3, kTaps3, C, 0);
     p.bias = F(h->b_fin); p.out = H(w.y);
-    const bool fuse_gn = gn_fusable(h, P, lT);
-    if (fuse_gn) {
-      gn_fill(h, P, lT, p, h->gnf_g, h->gnf_b);
-      p.temb = nullptr; p.out = H(w.h1);
-      if (int e = launch_gemm<256, EPI_GNA>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e;
-    }
-    else if (h->conv_bn == 128) { p.n_tiles = 2; p.m_major = 1; if (int e = launch_gemm<128, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
-    else { p.n_tiles = 1; if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e; }
+    p.n_tiles = 1;
+    if (int e = launch_gemm<256, EPI_STATS>(h, P.xF, P.xF, h->m_fin, p, stream, 2.0 * w.B * (double)w.T * C * 3 * C)) return e;
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
-    const int gn_rows = 4 * h->gn_rpw;
-    const dim3 gn_grid((lT.Lp + gn_rows - 1) / gn_rows, w.B);
-    if (!fuse_gn && can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, h->gn_rpw == 8 ? gn_apply_kernel<0, 8> : h->gn_rpw == 2 ? gn_apply_kernel<0, 2> : gn_apply_kernel<0, 4>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    const dim3 gn_grid((lT.Lp + GN_ROWS - 1) / GN_ROWS, w.B);
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -975,11 +855,8 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
   const WsLayout& w = P.w;
   char* ws = P.ws;
   auto Fw = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
-  // V^T pad columns [L, Lpad) are zeroed once with the whole workspace (get_plan) and never written afterwards
-  CUDA_TRY(cudaMemsetAsync(ws + w.flags, 0, 2ull * 4 * w.nflags, stream));   // inter-CTA flags of the fused GroupNorm launches
-  P.flag_par = 0;
   if (can_launch(h)) {
-    mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
+    mask_prep_kernel<<<w.B, 256, 0, stream>>>(mask, w.T, w.H, w.LpT, w.LpH, Fw(w.maskT), Fw(w.maskH), reinterpret_cast<int*>(ws + w.rowbT),
                                               reinterpret_cast<int*>(ws + w.rowbH), reinterpret_cast<int*>(ws + w.npadT),
                                               reinterpret_cast<int*>(ws + w.npadH));
     CUDA_TRY(cudaGetLastError());
@@ -988,7 +865,7 @@ static int run_prologue(MttsHandle* h, Plan& P, const float* x, const float* mu,
   if (can_launch(h)) {
     dim3 grid((w.LpT + 31) / 32, w.B);
     prep_x0_kernel<<<grid, 256, w.cinp * 33 * sizeof(float), stream>>>(
-        x, mu, spks, Fw(w.maskT), w.T, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
+        x, mu, spks, Fw(w.maskT), w.T, w.LpT, h->cfg.out_channels, h->nspk, w.cinp, reinterpret_cast<__half*>(ws + w.x0), 0);
     CUDA_TRY(cudaGetLastError());
     launched(h);
   }
@@ -1074,28 +951,18 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIRS")) h->cta_pairs = (e[0] == '1');
-  if (const char* e = getenv("MTTS_ATTN_V1")) h->attn_v2 = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_ATTN_V2")) h->attn_v3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
-  if (const char* e = getenv("MTTS_STAGGER")) h->stagger = (e[0] == '1');
-  if (const char* e = getenv("MTTS_BN")) h->conv_bn = atoi(e) == 128 ? 128 : 256;
-  if (const char* e = getenv("MTTS_BN_H")) h->conv_bn_h = atoi(e) == 128 ? 128 : 256;
-  if (const char* e = getenv("MTTS_NO_APREFETCH")) h->a_prefetch = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_NO_WHINT")) h->w_hint = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_LNQKV")) h->fused_lnqkv = (e[0] == '1');
-  if (const char* e = getenv("MTTS_GN_RPW")) h->gn_rpw = atoi(e) == 8 ? 8 : atoi(e) == 2 ? 2 : 4;
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_TAP3")) { h->tap3_plain = (e[0] != '2'); h->tap3_res = (e[0] != '1'); }
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
-  if (const char* e = getenv("MTTS_NO_TAIL")) h->fused_tail = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_GNFUSE")) h->fused_gn = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
     // on a GPU box: bind the device and opt the kernels into their dynamic shared memory sizes
+    if (device < 0 || device >= ndev) { delete h; return fail(MTTS_EINVAL, "device index out of range"); }
+    DeviceGuard dg(device);   // the caller's current device is restored on return
     cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    if (!dg.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
       delete h;
       return fail(MTTS_ECUDA, "cudaSetDevice / cudaGetDeviceProperties failed");
     }
@@ -1105,17 +972,12 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     int e = 0;
-    e |= set_gemm_attr<256, EPI_GNA>(); e |= set_gemm_attr<256, EPI_GNB>();
     e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
-    e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>(); e |= set_gemm_attr<256, EPI_LN>();
-    e |= set_gemm_attr<256, EPI_SNAKE>(); e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
-    e |= set_gemm_attr<128, EPI_PLAIN, 2>(); e |= set_gemm_attr<128, EPI_STATS, 2>(); e |= set_gemm_attr<128, EPI_PLAIN, 1>();
-    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) e = 1;
-    if (cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM) != cudaSuccess) e = 1;
+    e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>();
+    e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
-    if (cudaFuncSetAttribute(ln_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }
   } else {
     cudaGetLastError();  // no GPU: tables/sizes still work (used by the CPU-side tests); compute calls will fail
@@ -1126,10 +988,10 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
 
 void mtts_destroy(MttsHandle* h) {
   if (!h) return;
+  DeviceGuard dg(h->device);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   for (cudaStream_t st : h->side) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
-  for (cudaEvent_t ev : h->ev_turn) cudaEventDestroy(ev);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
@@ -1149,10 +1011,14 @@ int mtts_set_weight_arena(MttsHandle* h, void* dev_arena, size_t bytes, void* st
   if (!h || !dev_arena) return fail(MTTS_EINVAL, "null argument");
   if (bytes < h->arena_bytes) return fail(MTTS_ENOMEM, "weight arena too small (see mtts_weight_arena_bytes)");
   if ((reinterpret_cast<uintptr_t>(dev_arena) & 255) != 0) return fail(MTTS_EINVAL, "arena must be 256-byte aligned");
+  DEVICE_GUARD(h);
   h->arena = static_cast<char*>(dev_arena);
   CUDA_TRY(cudaMemsetAsync(dev_arena, 0, h->arena_bytes, static_cast<cudaStream_t>(stream)));
   for (auto& e : h->entries) e.loaded = false;
   h->plans.clear();
+  h->ws_nsub.clear();
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);   // they hold the old arena pointer and weight maps by value
+  h->graphs.clear();
   return build_weight_maps(h);
 }
 
@@ -1164,6 +1030,7 @@ int mtts_load_weight(MttsHandle* h, int idx, const float* src, int64_t numel, vo
   if (numel != e.numel)
     return fail(MTTS_EINVAL, "size mismatch for " + e.name + ": expected " + std::to_string(e.numel) + " elements, got " +
                                  std::to_string(numel));
+  DEVICE_GUARD(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   for (const PackOp& o : e.ops) {
     if (o.kind == 0) {
@@ -1197,6 +1064,22 @@ size_t mtts_workspace_bytes(const MttsHandle* h, int B, int T) {
   return total;
 }
 
+// drop the plans and graphs that live in [workspace, workspace + bytes)
+static void forget_workspace(MttsHandle* h, const void* workspace, size_t workspace_bytes) {
+  const char* lo = static_cast<const char*>(workspace);
+  const char* hi = lo + workspace_bytes;
+  for (auto it = h->plans.begin(); it != h->plans.end();) {
+    const char* w = static_cast<const char*>(std::get<0>(it->first));
+    if (w >= lo && w < hi) it = h->plans.erase(it);
+    else ++it;
+  }
+  for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+    const char* w = static_cast<const char*>(it->first.ws);
+    if (w >= lo && w < hi) { cudaGraphExecDestroy(it->second.first); it = h->graphs.erase(it); }
+    else ++it;
+  }
+}
+
 static int check_ready(MttsHandle* h) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
   if (!h->arena || !h->maps_ready) return fail(MTTS_ESTATE, "weight arena not set");
@@ -1214,10 +1097,10 @@ int mtts_estimator_forward(MttsHandle* h, const float* x, const float* mu, const
   if (!x || !mu || !mask || !t || !out || !workspace) return fail(MTTS_EINVAL, "null tensor argument");
   if ((h->nspk > 0) != (spks != nullptr))
     return fail(MTTS_EINVAL, "spks must be given iff in_channels > 2*out_channels");
+  DEVICE_GUARD(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Plan* P;
   if (int e = get_plan(h, workspace, workspace_bytes, B, T, stream, &P)) return e;
-  P->grid_cap = h->num_sms;
   h->launch_count = 0;
   CUDA_TRY(cudaMemcpyAsync(P->ws + P->w.tvals, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream));
   P->te_n = -1;  // per-utterance times: not a solver table
@@ -1244,85 +1127,12 @@ static int enqueue_solve(MttsHandle* h, Plan& P, float* z, const float* mu, cons
   return 0;
 }
 
-// One estimator evaluation of a solve: time-table row, destination, base and scale of the ODE update.
-struct EvalDesc { int t_idx; float* zout; const float* zbase; float zscale; };
-static void solve_evals(Plan& P, float* z, int n, int solver, std::vector<EvalDesc>* ev) {
-  const float dt = (float)(1.0 / (double)n);
-  float* zmid = reinterpret_cast<float*>(P.ws + P.w.zmid);
-  ev->clear();
-  for (int i = 0; i < n; ++i) {
-    if (solver == MTTS_SOLVER_EULER) ev->push_back(EvalDesc{i, z, z, dt});
-    else { ev->push_back(EvalDesc{2 * i, zmid, z, dt * 0.5f}); ev->push_back(EvalDesc{2 * i + 1, z, z, dt}); }
-  }
-}
-
-// Staggered schedule of the chains of one solve.  Per chain the work is  T_0 H_0 T_1 H_1 ... T_m  with
-// T_0 = prologue + head of evaluation 0, H_k = the level-T/2 part of evaluation k, T_k = tail of evaluation k-1 +
-// head of evaluation k.  The level-T blocks take turns across chains in the order (k, chain): chain c's T_k waits
-// for chain c-1's T_k, chain 0's T_k for the last chain's T_{k-1} -- while one chain holds the turn the others run
-// their level-T/2 blocks, whose kernels have half the row tiles, so the tiles of all running kernels fit the SMs.
-static int enqueue_solve_staggered(MttsHandle* h, const std::vector<Chunk>& chunks, std::vector<Plan*>& plans, float* z,
-                                   const float* mu, const float* mask, const float* spks, int n, int solver, int T,
-                                   cudaStream_t stream) {
-  const int nsub = (int)chunks.size();
-  const size_t NF = h->cfg.out_channels;
-  while ((int)h->ev_turn.size() < nsub) {
-    cudaEvent_t ev;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    h->ev_turn.push_back(ev);
-  }
-  CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
-  for (int i = 1; i < nsub; ++i) CUDA_TRY(cudaStreamWaitEvent(h->side[i - 1], h->ev_fork, 0));
-  std::vector<std::vector<EvalDesc>> evals(nsub);
-  for (int c = 0; c < nsub; ++c) {
-    if (plans[c]->te_n != n || plans[c]->te_solver != solver) return fail(MTTS_ESTATE, "internal: time-embedding table not prepared");
-    solve_evals(*plans[c], z + (size_t)chunks[c].b0 * NF * T, n, solver, &evals[c]);
-  }
-  const int m = (int)evals[0].size();
-  for (int k = 0; k <= m; ++k) {
-    for (int c = 0; c < nsub; ++c) {
-      const Chunk& ck = chunks[c];
-      Plan& P = *plans[c];
-      cudaStream_t st = c == 0 ? stream : h->side[c - 1];
-      if (k == 0) {
-        if (int e = run_prologue(h, P, z + (size_t)ck.b0 * NF * T, mu + (size_t)ck.b0 * NF * T, mask + (size_t)ck.b0 * T,
-                                 spks ? spks + (size_t)ck.b0 * h->nspk : nullptr, st))
-          return e;
-      }
-      if (!(k == 0 && c == 0)) {
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_turn[c > 0 ? c - 1 : nsub - 1], 0));
-        h->pdl_break = true;
-      }
-      if (k > 0) {
-        const EvalDesc& d = evals[c][k - 1];
-        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_TAIL)) return e;
-      }
-      if (k < m) {
-        const EvalDesc& d = evals[c][k];
-        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_HEAD)) return e;
-      }
-      h->pdl_break = false;
-      CUDA_TRY(cudaEventRecord(h->ev_turn[c], st));
-      if (k < m) {
-        const EvalDesc& d = evals[c][k];
-        if (int e = run_estimator(h, P, d.t_idx, 0, d.zout, d.zbase, d.zscale, true, st, EST_HALF)) return e;
-      }
-    }
-  }
-  for (int i = 1; i < nsub; ++i) {
-    CUDA_TRY(cudaEventRecord(h->ev_join[i - 1], h->side[i - 1]));
-    CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i - 1], 0));
-  }
-  return 0;
-}
-
 // all chains of one solve: chain 0 on `stream`, the others on forked side streams, joined at the end
 static int enqueue_solve_chains(MttsHandle* h, const std::vector<Chunk>& chunks, std::vector<Plan*>& plans, float* z,
                                 const float* mu, const float* mask, const float* spks, int n, int solver, int T,
                                 cudaStream_t stream) {
   const int nsub = (int)chunks.size();
   const size_t NF = h->cfg.out_channels;
-  if (nsub > 1 && h->stagger && h->launch_limit < 0) return enqueue_solve_staggered(h, chunks, plans, z, mu, mask, spks, n, solver, T, stream);
   if (nsub > 1) {
     CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
     for (int i = 1; i < nsub; ++i) CUDA_TRY(cudaStreamWaitEvent(h->side[i - 1], h->ev_fork, 0));
@@ -1349,19 +1159,26 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
     return fail(MTTS_EINVAL, "spks must be given iff in_channels > 2*out_channels");
   if (n < 1 || 2 * n > kMaxTimes) return fail(MTTS_EINVAL, "n_timesteps out of range [1, 1024]");
   if (solver != MTTS_SOLVER_EULER && solver != MTTS_SOLVER_MIDPOINT) return fail(MTTS_EINVAL, "unknown solver");
+  DEVICE_GUARD(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool debug_mode = h->launch_limit >= 0 || h->profiling;   // per-launch introspection: one chain
   const int nsub = debug_mode ? 1 : pick_nsub(h, B, T);
+  {
+    // The chain partition is laid over the workspace; plans (and graphs) built for another partition of the same
+    // memory claim regions the new one overwrites (zero guard rows, time tables): forget them first.
+    auto it = h->ws_nsub.find(workspace);
+    if (it != h->ws_nsub.end() && it->second != nsub) forget_workspace(h, workspace, workspace_bytes);
+    h->ws_nsub[workspace] = nsub;
+  }
   std::vector<Chunk> chunks;
   size_t need = 0;
-  if (!make_chunks(h, B, T, nsub, &chunks, &need)) return fail(MTTS_EINVAL, "unsupported shape: need B >= 1, T even and >= 2");
+  if (!make_chunks(h, B, T, nsub, &chunks, &need)) return fail(MTTS_EINVAL, "unsupported shape: need 1 <= B <= 2048 and T >= 1");
   if (workspace_bytes < need) return fail(MTTS_ENOMEM, "workspace too small (see mtts_workspace_bytes)");
   if (int e = ensure_side_streams(h, nsub)) return e;
   std::vector<Plan*> plans(nsub);
   for (int i = 0; i < nsub; ++i) {
     const size_t avail = (i + 1 < nsub ? chunks[i + 1].ws_off : need) - chunks[i].ws_off;
     if (int e = get_plan(h, static_cast<char*>(workspace) + chunks[i].ws_off, avail, chunks[i].nb, T, stream, &plans[i])) return e;
-    plans[i]->grid_cap = h->num_sms / nsub;   // concurrent chains: their flag-synchronised launches must all fit the SMs
   }
   h->launch_count = 0;
   for (int i = 0; i < nsub; ++i) {   // time-embedding tables: once per (plan, n_timesteps, solver), outside the graph
@@ -1406,27 +1223,21 @@ int mtts_euler_solve(MttsHandle* h, float* z, const float* mu, const float* mask
 
 int mtts_release_workspace(MttsHandle* h, const void* workspace, size_t workspace_bytes) {
   if (!h || !workspace) return fail(MTTS_EINVAL, "null argument");
-  const char* lo = static_cast<const char*>(workspace);
-  const char* hi = lo + workspace_bytes;
-  for (auto it = h->plans.begin(); it != h->plans.end();) {
-    const char* w = static_cast<const char*>(std::get<0>(it->first));
-    if (w >= lo && w < hi) it = h->plans.erase(it);
-    else ++it;
-  }
-  for (auto it = h->graphs.begin(); it != h->graphs.end();) {
-    const char* w = static_cast<const char*>(it->first.ws);
-    if (w >= lo && w < hi) { cudaGraphExecDestroy(it->second.first); it = h->graphs.erase(it); }
-    else ++it;
-  }
+  DEVICE_GUARD(h);
+  forget_workspace(h, workspace, workspace_bytes);
+  h->ws_nsub.erase(workspace);
   return 0;
 }
 
 int mtts_set_chains(MttsHandle* h, int n) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
   if (n < 0 || n > 8) return fail(MTTS_EINVAL, "chains must be in [0, 8]");
-  if (n != h->nsub_override) {   // the captured graphs embed the chain structure
+  if (n != h->nsub_override) {   // the captured graphs embed the chain structure, the plans the chain partition
+    DEVICE_GUARD(h);
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
     h->graphs.clear();
+    h->plans.clear();
+    h->ws_nsub.clear();
   }
   h->nsub_override = n;
   return 0;
@@ -1436,6 +1247,7 @@ int mtts_last_launch_count(const MttsHandle* h) { return h ? h->launch_count : 0
 
 int mtts_debug_profile_begin(MttsHandle* h, void* stream) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
+  DEVICE_GUARD(h);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->prof_events.clear(); h->prof_kind.clear(); h->prof_flops.clear();
   h->prof_stream = static_cast<cudaStream_t>(stream);
@@ -1445,6 +1257,7 @@ int mtts_debug_profile_begin(MttsHandle* h, void* stream) {
 
 int mtts_debug_profile_end(MttsHandle* h, int max_entries, float* ms, int* kind, double* flops) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
+  DEVICE_GUARD(h);
   h->profiling = false;
   if (!h->prof_events.empty()) CUDA_TRY(cudaEventSynchronize(h->prof_events.back()));
   const int n = (int)h->prof_kind.size();
@@ -1494,8 +1307,8 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
       {"maskT", w.maskT}, {"maskH", w.maskH}, {"rowbT", w.rowbT}, {"rowbH", w.rowbH}, {"npadT", w.npadT},
       {"npadH", w.npadH}, {"tvals", w.tvals}, {"te_e", w.te_e},   {"te_h1", w.te_h1}, {"te_h2", w.te_h2},
       {"te6", w.te6},     {"part", w.part},   {"x0", w.x0},       {"y", w.y},         {"res", w.res},
-      {"h1", w.h1},       {"xr", w.xr},       {"a", w.a},         {"xa", w.xa},       {"q", w.q},
-      {"k", w.k},         {"o", w.o},         {"vt", w.vt},       {"v", w.v},       {"s", w.s},         {"skip0", w.skip0},
+      {"h1", w.h1},       {"xr", w.xr},       {"a", w.a},         {"q", w.q},
+      {"k", w.k},         {"o", w.o},         {"v", w.v},       {"skip0", w.skip0},
       {"xD0", w.xD0},     {"skip1", w.skip1}, {"xD1", w.xD1},     {"xM0", w.xM0},     {"xM1", w.xM1},
       {"xU0s", w.xU0s},   {"xU0", w.xU0},     {"xU1s", w.xU1s},   {"xF", w.xF},       {"zmid", w.zmid}};
   auto it = m.find(name);
@@ -1505,10 +1318,10 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
 int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
                     int ntaps, const int* shifts, void* stream_) {
   if (!h || !A || !W || !out) return fail(MTTS_EINVAL, "null argument");
-  if (C % 64 || N % 128 || N > 1024 || (N % 256 && N > 512) || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
+  if (C % 64 || N % 256 || N > 1024 || ntaps < 1 || ntaps > GEMM_MAX_SEGS || rows < 1) return fail(MTTS_EINVAL, "bad gemm shape");
   if (int e = init_encode()) return e;
+  DEVICE_GUARD(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CUtensorMap ma, mw;
   GemmParams p{};
   p.M = rows; p.bias = bias; p.out = static_cast<__half*>(out); p.ldo = N; p.mask_mul = 1;
   if (const char* e = getenv("MTTS_DBG")) p.dbg = atoi(e);
@@ -1516,20 +1329,11 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
   const int saved = h->launch_limit;
   h->launch_limit = -1;
   int e;
-  if (N % 256 == 0) {
-    TMap ta, tw;   // production 256-wide path (CTA pairs unless MTTS_NO_PAIRS=1)
+  {
+    TMap ta, tw;   // production 256-wide path (CTA pairs with MTTS_PAIRS=1)
     if (make_tmap(&ta, A, rows, C, C, 128) || make_tmap(&tw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 256)) return MTTS_ECUDA;
     p.n_tiles = N / 256;
     e = launch_gemm<256, EPI_PLAIN>(h, ta, ta, tw, p, stream);
-  } else if (C % 128 == 0) {   // production 128-wide path: two K chunks per stage through the 3-D maps
-    TMap ta, tw;
-    if (make_tmap(&ta, A, rows, C, C, 128) || make_tmap(&tw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;
-    p.n_tiles = N / 128;
-    e = launch_gemm<128, EPI_PLAIN>(h, ta, ta, tw, p, stream);
-  } else {
-    if (make_map(&ma, A, rows, C, C, 128) || make_map(&mw, W, N, (uint64_t)ntaps * C, (uint64_t)ntaps * C, 128)) return MTTS_ECUDA;
-    p.n_tiles = N / 128;
-    e = launch_gemm_maps<128, EPI_PLAIN, 1>(h, ma, ma, mw, p, stream, 0.0);
   }
   h->launch_limit = saved;
   return e;

@@ -156,11 +156,14 @@ class _Engine:
         self.device = device
         self.cfg = cfg
         h = C.c_void_p()
+        # the library binds everything to the handle's device and restores the caller's current device (DeviceGuard in
+        # mtts_api.cu); the torch-side allocations below are made under the same device for symmetry
         _lib.check(self.lib.mtts_create(C.byref(cfg), device.index or 0, C.byref(h)))
         self.h = h
         self.n_weights = self.lib.mtts_num_weights(h)
         self.names = [self.lib.mtts_weight_name(h, i).decode() for i in range(self.n_weights)]
-        self.arena, self.arena_ptr = _aligned_buffer(self.lib.mtts_weight_arena_bytes(h), device, 256)
+        with torch.cuda.device(device):
+            self.arena, self.arena_ptr = _aligned_buffer(self.lib.mtts_weight_arena_bytes(h), device, 256)
         self.ws: Dict[Tuple[int, int], Tuple[torch.Tensor, int, int]] = {}
         self.static: Dict[tuple, dict] = {}
         self.side_stream = None
@@ -168,6 +171,7 @@ class _Engine:
 
     def __del__(self):
         try:
+            torch.cuda.synchronize(self.device)     # nothing enqueued may still use the handle's graphs / arena
             self.lib.mtts_destroy(self.h)
         except Exception:
             pass
@@ -184,7 +188,8 @@ class _Engine:
             keep.append(src)
             _lib.check(self.lib.mtts_load_weight(self.h, i, src.data_ptr(), src.numel(), st))
         torch.cuda.current_stream(self.device).synchronize()   # `keep` may be freed afterwards
-        self.ws.clear()
+        for key in list(self.ws):                              # plans and graphs captured over the old weights are gone
+            self._drop_shape(key)
         self.static.clear()
 
     MAX_SHAPES = 24     # workspaces (and static graph buffers) kept per engine; least recently used shapes are dropped
@@ -194,7 +199,7 @@ class _Engine:
         if key not in self.ws:
             n = self.lib.mtts_workspace_bytes(self.h, B, T)
             if n == 0:
-                raise _lib.MttsError(f"unsupported shape B={B}, T={T}: T must be even and >= 2")
+                raise _lib.MttsError(f"unsupported shape B={B}, T={T}: need 1 <= B <= 2048 and T >= 1")
             while len(self.ws) >= self.MAX_SHAPES:           # bucketed serving sees many (B, T): bound the memory
                 old = next(iter(self.ws))
                 self._drop_shape(old)

@@ -39,9 +39,9 @@ def _d(x):
 # unit: the tcgen05 implicit-GEMM kernel vs fp32 matmul of the same fp16 operands
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rows,Cc,N,shifts", [
-    (1, 64, 128, [0]), (127, 64, 256, [0]), (128, 192, 256, [-1, 0, 1]), (129, 256, 256, [-1, 0, 1]),
+    (1, 64, 256, [0]), (127, 64, 256, [0]), (128, 192, 256, [-1, 0, 1]), (129, 256, 256, [-1, 0, 1]),
     (22144, 256, 256, [-1, 0, 1]), (11072, 512, 256, [0]), (5000, 256, 1024, [0]), (3000, 1024, 256, [0]),
-    (4097, 128, 384, [0]), (777, 256, 512, [-1, 0, 1]),
+    (4097, 128, 512, [0]), (777, 256, 512, [-1, 0, 1]), (300, 192, 768, [-2, -1, 0, 1, 2]),
 ])
 def test_gemm_tc(lj, rows, Cc, N, shifts):
     dec, _, _ = lj
@@ -181,12 +181,25 @@ def test_estimator_stage_trace():
     (160, 4, 344, [344, 331, 312, 300], 10, 23),       # config 2, bucketed ragged lengths
     (160, 4, 344, [344, 331, 312, 300], 2, 24),        # config 3 sweep ends
     (160, 2, 344, None, 50, 25),
-    (160, 2, 1024, None, 10, 26),                      # config 4 regime (multi-tile attention), reduced T for CPU time
+    (160, 2, 1024, None, 10, 26),                      # config 4 regime (multi-tile attention) at a second T
     (160, 2, 1024, [1024, 700], 10, 27),
     (224, 4, 200, [200, 180, 64, 133], 10, 28),        # config 5: multi-speaker
+    (160, 64, 344, None, 10, 2),                       # config 2 at its NAMED shape: B64 x T344, all rows full length
+    (160, 64, 344, "U300..344", 10, 2),                # ... and bucketed ragged lengths U{300..344}, >= 1 full row (seed 2)
+    (160, 16, 2048, None, 10, 4),                      # config 4 at its NAMED shape: B16 x T2048, every row real attention
+    (160, 16, 2048, "U512..2048", 10, 4),              # ... and lengths U{512..2048} rounded like fix_len_compatibility (seed 4)
+    (160, 3, 345, [345, 345, 301], 10, 29),            # odd T: the reference's nearest-resize crop (model.py:1027-1028)
 ])
 def test_ten_step_parity(lj, vctk, cin, B, T, lengths, n, seed):
     dec, cfg, sd = lj if cin == 160 else vctk
+    if isinstance(lengths, str):                       # seeded uniform lengths, one full-length row
+        lo = int(lengths[1:].split("..")[0])
+        g = torch.Generator().manual_seed(seed)
+        lengths = torch.randint(lo, T + 1, (B,), generator=g)
+        if T >= 512:
+            lengths = ((lengths + 3) // 4) * 4         # fix_len_compatibility rounding (model.py:49-55)
+        lengths[0] = T
+        lengths = lengths.tolist()
     mu, mask, z0, spks = O.make_inputs(cfg, B, T, lengths, seed=seed)
     zr = O.euler_solve(sd, cfg, z0, mu, mask, n, spks)
     z = dec.solve(_d(z0), _d(mu), _d(mask), n, _d(spks), "euler", use_graph=True).cpu()
@@ -211,7 +224,9 @@ def test_midpoint_and_graph_equivalence(lj):
 # edge cases of the reference's contract
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,T,lengths", [(1, 2, None), (2, 4, [4, 1]), (3, 6, [6, 6, 2]), (1, 30, None),
-                                         (5, 34, [34, 33, 2, 17, 1]), (2, 130, [130, 129]), (1, 258, None), (1, 384, None)])
+                                         (5, 34, [34, 33, 2, 17, 1]), (2, 130, [130, 129]), (1, 258, None), (1, 384, None),
+                                         (1, 1, None), (2, 3, [3, 2]), (1, 33, None), (3, 35, [35, 34, 9]), (2, 129, [129, 77]),
+                                         (1, 343, None)])
 def test_small_and_ragged_shapes(lj, B, T, lengths):
     dec, cfg, sd = lj
     mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=B * 100 + T)
@@ -241,8 +256,9 @@ def test_invalid_shapes_raise(lj):
     dec, cfg, _ = lj
     from matcha_tts_b200._lib import MttsError
     z = torch.zeros(1, 80, 33, device="cuda")
-    with pytest.raises(MttsError):                                   # odd T is not supported by the native path
-        dec(z, torch.ones(1, 1, 33, device="cuda"), z, torch.zeros(1, device="cuda"))
+    with pytest.raises(MttsError):                                   # more utterances than the time table holds
+        big = torch.zeros(2049, 80, 4, device="cuda")
+        dec(big, torch.ones(2049, 1, 4, device="cuda"), big, torch.zeros(2049, device="cuda"))
     with pytest.raises(ValueError):
         dec(z[:, :40], torch.ones(1, 1, 33, device="cuda"), z[:, :40], torch.zeros(1, device="cuda"))
     with pytest.raises(ValueError):                                   # spks given to a single-speaker estimator
@@ -420,15 +436,12 @@ def test_chains_setting_keeps_results(lj):
 # ---------------------------------------------------------------------------------------------
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env", ["MTTS_GNFUSE", "MTTS_LNQKV", "MTTS_STAGGER", "MTTS_NO_TAIL", "MTTS_NO_PDL", "MTTS_PAIRS",
-                                 "MTTS_ATTN_V1", "MTTS_ATTN_V2", "MTTS_PDL_EARLY", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3"])
+@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_PDL_EARLY", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3"])
 def test_opt_in_variants(env):
     old = os.environ.get(env)
     os.environ[env] = "1"
     if env == "MTTS_PAIRS":
         os.environ["MTTS_PAIR_MIN_CHUNKS"] = "0"
-    if env == "MTTS_STAGGER":
-        os.environ["MTTS_NSUB"] = "2"
     try:
         dec, cfg, sd = U.make_decoder(160)
         mu, mask, z0, _ = O.make_inputs(cfg, 3, 344, [344, 301, 222], seed=80)
@@ -442,9 +455,68 @@ def test_opt_in_variants(env):
             for rows, Cc, N, shifts in [(129, 256, 256, [-1, 0, 1]), (5000, 256, 1024, [0]), (777, 512, 512, [-1, 0, 1])]:
                 _check_gemm(eng, rows, Cc, N, shifts)
     finally:
-        os.environ.pop("MTTS_NSUB", None)
         os.environ.pop("MTTS_PAIR_MIN_CHUNKS", None)
         if old is None:
             os.environ.pop(env, None)
         else:
             os.environ[env] = old
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16 range: trained checkpoints are not random-init sized
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scale,alpha", [(2.0, 1.0), (4.0, 2.0)])
+def test_weight_scale_stress(scale, alpha):
+    """Every conv / linear WEIGHT of the estimator scaled by 2 or 4 and the SnakeBeta log-frequencies raised
+    (exp(alpha) up to e^2): pre-GroupNorm conv outputs, q.k scores and the FF1 intermediate grow by the same factors.
+    Activations are stored as fp16 (max 65504); the normalisation layers bound everything except the FF1 / SnakeBeta
+    intermediate, which saturates instead of overflowing (ptx.cuh pack_h2_sat).  The result must stay finite and inside
+    the parity bar of BASELINE.json against the fp32 oracle with the same weights."""
+    cfg = O.DecoderCfg()
+    sd = O.make_state_dict(cfg, 0)
+    for k in sd:
+        leaf = k.rsplit(".", 1)[-1]
+        is_norm = (".block.1." in k) or (".norm1." in k) or (".norm3." in k)
+        if leaf == "weight" and not is_norm and not k.startswith("time_mlp"):
+            sd[k] = sd[k] * scale
+        if leaf == "alpha":
+            sd[k] = sd[k] + alpha
+    from matcha_tts_b200 import Decoder
+    dec = Decoder(in_channels=160, out_channels=80, channels=(256, 256), num_heads=2, num_mid_blocks=2)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda()
+    mu, mask, z0, _ = O.make_inputs(cfg, 3, 128, [128, 128, 90], seed=90)
+    t = torch.tensor([0.1, 0.5, 0.9])
+    ref = O.estimator_forward(sd, cfg, z0, mask, mu, t)
+    est = dec(_d(z0), _d(mask), _d(mu), _d(t)).cpu()
+    assert torch.isfinite(est).all()
+    ma, rl = O.parity_errors(est, ref, mask)
+    print(f"weights x{scale}, alpha +{alpha}: estimator max-abs {ma:.2e} rel-L2 {rl:.2e} (|ref| max {float(ref.abs().max()):.2f})")
+    assert rl <= EST_REL, (ma, rl)
+    zr = O.euler_solve(sd, cfg, z0, mu, mask, 10)
+    z = dec.solve(_d(z0), _d(mu), _d(mask), 10, None, "euler", use_graph=False).cpu()
+    assert torch.isfinite(z).all()
+    ma, rl = O.parity_errors(z, zr, mask)
+    print(f"weights x{scale}, alpha +{alpha}: 10-step max-abs {ma:.2e} rel-L2 {rl:.2e}")
+    assert ma <= O.TOL_MAX_ABS * max(1.0, float(zr.abs().max()) / 4.0) and rl <= O.TOL_REL_L2, (ma, rl)
+
+
+# ---------------------------------------------------------------------------------------------
+# the handle's device is not the caller's current device (ADVICE r1: cudaSetDevice leak)
+# ---------------------------------------------------------------------------------------------
+def test_current_device_is_preserved(lj):
+    dec, cfg, sd = lj
+    before = torch.cuda.current_device()
+    mu, mask, z0, _ = O.make_inputs(cfg, 2, 32, [32, 20], seed=95)
+    dec.solve(_d(z0), _d(mu), _d(mask), 2, None, "euler", use_graph=True)
+    assert torch.cuda.current_device() == before
+    if torch.cuda.device_count() < 2:
+        return
+    # tensors and engine on cuda:1 while cuda:0 stays current: kernels, side streams and graphs must bind to cuda:1
+    dec1, _, _ = U.make_decoder(160, device="cuda:1")
+    zr = O.euler_solve(sd, cfg, z0, mu, mask, 3)
+    for use_graph in (False, True):
+        z = dec1.solve(z0.to("cuda:1"), mu.to("cuda:1"), mask.to("cuda:1"), 3, None, "euler", use_graph=use_graph)
+        assert z.device == torch.device("cuda:1") and torch.cuda.current_device() == before
+        ma, rl = O.parity_errors(z.cpu(), zr, mask)
+        assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)

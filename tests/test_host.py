@@ -52,7 +52,8 @@ def test_weight_table_matches_state_dict(libmtts, cin):
     # workspace sizing: valid and invalid shapes
     assert libmtts.mtts_workspace_bytes(h, 64, 344) > 0
     assert libmtts.mtts_workspace_bytes(h, 1, 2) > 0
-    assert libmtts.mtts_workspace_bytes(h, 4, 33) == 0          # odd T
+    assert libmtts.mtts_workspace_bytes(h, 4, 33) > libmtts.mtts_workspace_bytes(h, 4, 32)   # odd T: one more guard row (reference crop, model.py:1027)
+    assert libmtts.mtts_workspace_bytes(h, 4, 0) == 0
     assert libmtts.mtts_workspace_bytes(h, 0, 32) == 0
     assert libmtts.mtts_debug_buffer_offset(h, 2, 32, 0, b"skip0") > 0
     assert libmtts.mtts_debug_buffer_offset(h, 2, 32, 0, b"nope") == -1
@@ -199,5 +200,7 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "mel-frames/s" and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "model.py"))    # tools/stage_reference.sh
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["config"]["config1_cpu"]["batch"] == 1 and d["config"]["config1_cpu"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
