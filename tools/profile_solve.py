@@ -10,12 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from matcha_tts_b200 import Decoder, _lib  # noqa: E402
 
-GNFUSE = os.environ.get("MTTS_GNFUSE") == "1"      # GroupNorm-apply inside the conv launches (opt-in experiment)
-if GNFUSE:
-    NAMES = ["conv1", "conv2", "qkv", "attn"]
-else:
-    NAMES = ["conv1", "gnA", "conv2"] + (["lnqkv"] if os.environ.get("MTTS_LNQKV") == "1" and os.environ.get("MTTS_NO_TAIL") != "1" else ["gnB", "qkv"]) + ["attn"]
-NAMES += ["to_out", "ff1", "ff2"] if os.environ.get("MTTS_NO_TAIL") == "1" else ["tail"]
+# launches of one resnet + transformer stage, in order (switches as in mtts_create)
+NAMES = ["conv1"] + ([] if os.environ.get("MTTS_GNA_SPLIT") == "0" else ["gnA"]) + ["conv2"]
+NAMES += ["gnbqkv"] if os.environ.get("MTTS_GNBQKV") == "1" else ["gnB", "qkv"]
+NAMES += ["attn", "tail"]
 
 
 def labels():
@@ -25,7 +23,7 @@ def labels():
         per_step += [f"s{s}.{n}" for n in NAMES]
         if s in (0, 1, 4, 5):
             per_step.append(f"s{s}.levelconv")
-    per_step += ["final.conv", "final.proj"] if GNFUSE else ["final.conv", "final.gn", "final.proj"]
+    per_step += ["final.conv", "final.gn", "final.proj"]
     return out, per_step
 
 
