@@ -224,6 +224,7 @@ struct MttsHandle {
                             // measured equal at full occupancy (70 vs 73 us at level T, 46 vs 45 us at level T/2, B=256) and slower for one
                             // solve at a time (3.55 vs 3.75 M frames/s): its transform runs on 8 warps per SM at ~0.4 IPC per scheduler
                             // partition while the stand-alone pass has ~40 warps per SM -- profiles/r02_gnbqkv_*.txt
+  bool sleep_wait = false;  // MTTS_SLEEPWAIT=1: TMA producer warps sleep between polls of their ring slots
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
   bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
@@ -567,6 +568,7 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   pp.w_hint = h->w_hint ? 1 : 0;
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
   pp.pdl_late = h->pdl_late ? 1 : 0;
+  pp.sleep_wait = h->sleep_wait ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
                     wmap, pp));
@@ -596,6 +598,7 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
         GemmParams pp = p;
         pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
         pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
+        pp.sleep_wait = h->sleep_wait ? 1 : 0;
         CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
                                stream, a0.d2, a1.d2, wmap.d2h, pp));
         launched(h);
@@ -742,7 +745,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
     tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
     tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
-    tp.tl = h->tail_tl;
+    tp.tl = h->tail_tl; tp.sleep_wait = h->sleep_wait ? 1 : 0;
     const int tiles = (lc.rows + 127) / 128;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     if (h->tail_pairs) {
@@ -979,6 +982,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
+  if (const char* e = getenv("MTTS_SLEEPWAIT")) h->sleep_wait = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {

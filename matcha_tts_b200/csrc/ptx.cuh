@@ -67,6 +67,11 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   }
 }
 
+__device__ __forceinline__ void mbar_wait_opt(uint64_t* bar, uint32_t parity, int sleep) {
+  if (sleep) mbar_wait_sleep(bar, parity);
+  else mbar_wait(bar, parity);
+}
+
 // ------------------------------------------------------------------ CTA pairs (cluster of 2, tcgen05 cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
