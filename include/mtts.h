@@ -142,6 +142,53 @@ int64_t mtts_debug_buffer_offset(const MttsHandle* h, int B, int T, int level, c
 int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bias, void* out, int rows, int C, int N,
                     int ntaps, const int* shifts, void* stream);
 
+/* ---- the step before the path: TextEncoder + duration predictor ----------------------
+ * Replaces the body of TextEncoder.forward(x, x_lengths, spks) -> (mu, logw, x_mask)          reference model.py:500-535
+ * (embedding, ConvReluNorm prenet :168-207, RoPE transformer encoder :244-438, proj_m, DurationPredictor :209-235).
+ * Same conventions as above: caller-owned buffers, no allocation, no synchronisation, errors as codes.
+ *   tokens  (B, T_x) int64 symbol ids          lengths (B,) int64          spks (B, spk_emb_dim) fp32, already embedded, or NULL
+ *   mu (B, n_feats, T_x) fp32      logw (B, 1, T_x) fp32      x_mask (B, 1, T_x) fp32 0/1
+ * Supported: n_channels and n_channels + spk_emb_dim (when n_spks > 1) multiples of 64 and <= 256; (width / n_heads) in
+ * {32, 64, 96, 128}; filter_channels in {256, 512, 768, 1024}; filter_channels_dp = 256; kernel_size = kernel_size_dp = 3
+ * (the prenet's kernel 5 and 3 layers are fixed by the reference, model.py:463-471); n_feats <= 256.
+ * The weight table lists the reference's state-dict keys of `TextEncoder` (MatchaTTS prefix `encoder.`) in a fixed order;
+ * "@rope_theta" is host-derived: 1 / 10000^(arange(0, d, 2) / d), d = (width / n_heads) / 2 (model.py:262, :319-320). */
+typedef struct MttsTextHandle MttsTextHandle;
+typedef struct MttsTextConfig {
+  int n_vocab;
+  int n_feats;
+  int n_channels;
+  int filter_channels;
+  int n_heads;
+  int n_layers;
+  int kernel_size;
+  int prenet;              /* 0 / 1 */
+  int filter_channels_dp;
+  int kernel_size_dp;
+  int n_spks;
+  int spk_emb_dim;
+} MttsTextConfig;
+
+int mtts_text_create(const MttsTextConfig* cfg, int device, MttsTextHandle** out);
+void mtts_text_destroy(MttsTextHandle* h);
+int mtts_text_num_weights(const MttsTextHandle* h);
+const char* mtts_text_weight_name(const MttsTextHandle* h, int idx);
+int64_t mtts_text_weight_numel(const MttsTextHandle* h, int idx);
+size_t mtts_text_weight_arena_bytes(const MttsTextHandle* h);
+int mtts_text_set_weight_arena(MttsTextHandle* h, void* dev_arena, size_t bytes, void* stream);
+int mtts_text_load_weight(MttsTextHandle* h, int idx, const float* dev_src, int64_t numel, void* stream);
+int mtts_text_weights_loaded(const MttsTextHandle* h);
+size_t mtts_text_workspace_bytes(const MttsTextHandle* h, int B, int T_x);
+int mtts_text_release_workspace(MttsTextHandle* h, const void* workspace, size_t workspace_bytes);
+int mtts_text_encoder_forward(MttsTextHandle* h, const int64_t* tokens, const int64_t* lengths, const float* spks, float* mu,
+                              float* logw, float* x_mask, void* workspace, size_t workspace_bytes, int B, int T_x, void* stream);
+int mtts_text_last_launch_count(const MttsTextHandle* h);
+/* introspection used by the parity tests: stop after n kernel launches (n < 0: run everything); byte offset of a named
+ * intermediate ("X", "X1", "Y", "H", "O", "QKV", "F": fp16 rows of 256 / 768 / filter_channels columns, T_x + 2 rows per
+ * utterance) inside the workspace for (B, T_x), -1 for an unknown name */
+int mtts_text_debug_set_launch_limit(MttsTextHandle* h, int n);
+int64_t mtts_text_debug_buffer_offset(const MttsTextHandle* h, int B, int T_x, const char* name);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,11 @@ class MttsConfig(C.Structure):
                 ("heads", C.c_int), ("head_dim", C.c_int), ("n_mid_blocks", C.c_int)]
 
 
+class MttsTextConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_vocab", "n_feats", "n_channels", "filter_channels", "n_heads", "n_layers", "kernel_size",
+                                       "prenet", "filter_channels_dp", "kernel_size_dp", "n_spks", "spk_emb_dim")]
+
+
 class MttsError(RuntimeError):
     pass
 
@@ -56,6 +61,21 @@ SIGNATURES = {
     "mtts_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "mtts_debug_set_tile_timeline": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtts_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    "mtts_text_create": (C.c_int, [C.POINTER(MttsTextConfig), C.c_int, C.POINTER(C.c_void_p)]),
+    "mtts_text_destroy": (None, [C.c_void_p]),
+    "mtts_text_num_weights": (C.c_int, [C.c_void_p]),
+    "mtts_text_weight_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "mtts_text_weight_numel": (C.c_int64, [C.c_void_p, C.c_int]),
+    "mtts_text_weight_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "mtts_text_set_weight_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mtts_text_load_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mtts_text_weights_loaded": (C.c_int, [C.c_void_p]),
+    "mtts_text_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "mtts_text_release_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mtts_text_encoder_forward": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+    "mtts_text_last_launch_count": (C.c_int, [C.c_void_p]),
+    "mtts_text_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "mtts_text_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "mtts_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
 }

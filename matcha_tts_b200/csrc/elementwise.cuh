@@ -284,13 +284,14 @@ __global__ void pack2d_kernel(const float* __restrict__ src, __half* __restrict_
   const int n = (int)(i / C), c = (int)(i % C);
   dst[(size_t)(n + n_off) * ldd + k_off + c] = __float2half_rn(scale * src[n * sn + c * sc + off]);
 }
-// mode 0: copy; 1: exp(x); 2: 1/(exp(x)+1e-9)
-__global__ void packf_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int mode) {
+// mode 0: scale * x; 1: exp(x); 2: 1/(exp(x)+1e-9)
+__global__ void packf_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int mode, float scale) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = src[i];
   if (mode == 1) v = expf(v);
   else if (mode == 2) v = 1.0f / (expf(v) + 1e-9f);
+  else v = scale * v;
   dst[i] = v;
 }
 

@@ -105,6 +105,7 @@ struct GemmParams {
                    //    res_chunk0 on).  tmA0 / tmA1 then have 130-row boxes and one (128 + 2)-row activation tile per K chunk feeds
                    //    all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu); the res_conv pass
                    //    stages the tiles once more and reads them one row in
+  int relu;        // EPI_PLAIN: 1 = ReLU after bias (+ residual), before the row mask (text encoder FFN / duration predictor convs)
   int sleep_wait;  // 1: the TMA producer warps sleep between polls of their ring slots instead of spinning (the polls compete with
                    //    the epilogue warps of their scheduler partitions for issue slots)
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
@@ -592,6 +593,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             gs[2 * c] = a0; gs[2 * c + 1] = b0;
           }
           if constexpr (EPI == EPI_PLAIN) {
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }

@@ -265,9 +265,9 @@ static PackOp op_h(size_t dst, int N, int C, long sn, long sc, long off, int n_o
   o.n_off = n_off; o.ldd = ldd; o.k_off = k_off; o.scale = scale;
   return o;
 }
-static PackOp op_f(size_t dst, int n, int mode = 0) {
+static PackOp op_f(size_t dst, int n, int mode = 0, float scale = 1.f) {
   PackOp o{};
-  o.kind = 1; o.dst = dst; o.N = n; o.mode = mode;
+  o.kind = 1; o.dst = dst; o.N = n; o.mode = mode; o.scale = scale;
   return o;
 }
 
@@ -1067,7 +1067,7 @@ int mtts_load_weight(MttsHandle* h, int idx, const float* src, int64_t numel, vo
       pack2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
           src, reinterpret_cast<__half*>(h->arena + o.dst), o.N, o.C, o.sn, o.sc, o.off, o.n_off, o.ldd, o.k_off, o.scale);
     } else {
-      packf_kernel<<<(o.N + 255) / 256, 256, 0, stream>>>(src, reinterpret_cast<float*>(h->arena + o.dst), o.N, o.mode);
+      packf_kernel<<<(o.N + 255) / 256, 256, 0, stream>>>(src, reinterpret_cast<float*>(h->arena + o.dst), o.N, o.mode, o.scale);
     }
     CUDA_TRY(cudaGetLastError());
   }
@@ -1369,3 +1369,5 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
 }
 
 }  // extern "C"
+
+#include "mtts_text.inc"

@@ -446,13 +446,14 @@ class CFM(BASECFM):
 # model facade: the boundary the hot path is called through
 # ----------------------------------------------------------------------------------------------
 class MatchaTTS(nn.Module):
-    """Facade with the reference's `synthesize` signature (model.py:1173-1300).
+    """The reference's model class (model.py:1172-1300): same constructor, module tree / state-dict keys (`encoder.*`,
+    `decoder.estimator.*`, `spk_emb.weight`, `mel_mean`, `mel_std`) and `synthesize` signature.
 
-    The text encoder / duration predictor (model.py:148-535) is outside this hot path
-    (SURVEY.md section 8f row 1): pass any module with the reference TextEncoder interface
-    `encoder(x, x_lengths, spks) -> (mu, logw, x_mask)` -- e.g. the reference's own -- as
-    `encoder=`.  Everything from the durations to the mel (model.py:1272-1300) is implemented here
-    around the native decoder.
+    `self.encoder` is the native TextEncoder + duration predictor (text_encoder.py; model.py:441-535), `self.decoder` the
+    native CFM sampler; the glue between them -- durations -> lengths -> hard alignment -> mu_y -> denormalize -> crop
+    (model.py:1272-1300) -- is a handful of torch calls.  `encoder=` substitutes any module with the TextEncoder interface
+    `encoder(x, x_lengths, spks) -> (mu, logw, x_mask)`; with `encoder_params` that only carry `n_feats` and no `encoder=`
+    the model is decoder-only and `synthesize` raises.
     """
 
     def __init__(self, n_vocab, n_spks, spk_emb_dim, encoder_params, decoder_params, cfm_params,
@@ -467,6 +468,11 @@ class MatchaTTS(nn.Module):
         self.register_buffer("mel_std", torch.tensor(1.0))
         if encoder is not None:
             self.encoder = encoder
+        elif hasattr(encoder_params, "n_channels"):
+            from .text_encoder import TextEncoder
+            self.encoder = TextEncoder(encoder_type=getattr(encoder_params, "encoder_type", "RoPE Encoder"),
+                                       encoder_params=encoder_params, duration_predictor_params=duration_predictor_params,
+                                       n_vocab=n_vocab, n_spks=n_spks, spk_emb_dim=spk_emb_dim)
         n_feats = encoder_params.n_feats
         in_ch = 2 * n_feats + (spk_emb_dim if n_spks > 1 else 0)
         est = Decoder(in_channels=in_ch, out_channels=n_feats, channels=decoder_params.channels,
@@ -479,8 +485,8 @@ class MatchaTTS(nn.Module):
     @torch.inference_mode()
     def synthesize(self, x, x_lengths, n_timesteps, temperature=1.0, spks=None, length_scale=1.0):
         if not hasattr(self, "encoder"):
-            raise RuntimeError("MatchaTTS.synthesize needs a text encoder: pass encoder= (out of scope of the "
-                               "native hot path, see class docstring)")
+            raise RuntimeError("this MatchaTTS was built decoder-only (encoder_params without n_channels and no encoder=): "
+                               "synthesize needs the text encoder, see the class docstring")
         mu, logw, x_mask = self.encoder(x, x_lengths, spks)
         w = torch.exp(logw) * x_mask * length_scale
         w_ceil = torch.ceil(w)

@@ -204,3 +204,56 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["config"]["config1_cpu"]["batch"] == 1 and d["config"]["config1_cpu"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("n_spks", [1, 109])
+def test_text_weight_table_matches_state_dict(libmtts, n_spks):
+    """The text encoder's weight table (mtts_text_weight_name / _numel) lists the reference TextEncoder's state-dict keys
+    (oracle.param_shapes == the live reference's, tests/test_text_oracle.py) in a fixed order, plus the host-derived RoPE
+    frequencies; the package's spec mirrors it."""
+    from matcha_tts_b200 import _lib
+    from matcha_tts_b200.text_encoder import text_encoder_param_spec
+    from oracle import text_encoder_oracle as TO
+    cfg = TO.TextEncCfg(n_spks=n_spks)
+    tc = _lib.MttsTextConfig(cfg.n_vocab, cfg.n_feats, cfg.n_channels, cfg.filter_channels, cfg.n_heads, cfg.n_layers, cfg.kernel_size, 1,
+                             cfg.filter_channels_dp, cfg.kernel_size_dp, n_spks, cfg.spk_emb_dim)
+    h = C.c_void_p()
+    _lib.check(libmtts.mtts_text_create(C.byref(tc), 0, C.byref(h)))
+    table = [(libmtts.mtts_text_weight_name(h, i).decode(), libmtts.mtts_text_weight_numel(h, i)) for i in range(libmtts.mtts_text_num_weights(h))]
+    shapes = TO.param_shapes(cfg)
+    spec = text_encoder_param_spec(cfg.n_vocab, cfg.n_channels, cfg.filter_channels, cfg.n_layers, cfg.kernel_size, True, cfg.n_feats,
+                                   cfg.filter_channels_dp, cfg.kernel_size_dp, cfg.width)
+    assert dict(spec) == shapes and [k for k, _ in spec] == list(shapes)
+    half = (cfg.width // cfg.n_heads) // 4
+    want = [(k, int(torch.Size(s).numel())) for k, s in spec]
+    want.insert(1, ("@rope_theta", half))
+    assert table == want
+    assert libmtts.mtts_text_workspace_bytes(h, 64, 120) > 0 and libmtts.mtts_text_workspace_bytes(h, 0, 5) == 0
+    assert libmtts.mtts_text_load_weight(h, 0, C.c_void_p(16), cfg.n_vocab * cfg.n_channels, None) == -3      # arena not set
+    libmtts.mtts_text_destroy(h)
+    bad = _lib.MttsTextConfig(178, 80, 200, 768, 2, 6, 3, 1, 256, 3, 1, 64)                                      # width not a multiple of 64
+    h2 = C.c_void_p()
+    assert libmtts.mtts_text_create(C.byref(bad), 0, C.byref(h2)) == -1 and b"multiples of 64" in libmtts.mtts_last_error()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_matcha_state_dict_equals_reference_and_loads_a_lightning_checkpoint():
+    """The whole model tree -- native text encoder, estimator, buffers -- has the reference MatchaTTS's keys and shapes, so
+    a reference training checkpoint loads with strict=True (reference main.py:94-121)."""
+    from matcha_tts_b200 import MatchaTTS, load_lightning_checkpoint
+    ref = _ref()
+    enc = types.SimpleNamespace(encoder_type="RoPE Encoder", n_feats=80, n_channels=192, filter_channels=768, n_heads=2, n_layers=6,
+                                kernel_size=3, p_dropout=0.1, prenet=True)
+    dec = types.SimpleNamespace(channels=(256, 256), dropout=0.05, attention_head_dim=64, n_blocks=1, num_mid_blocks=2, num_heads=2,
+                                act_fn="snakebeta")
+    dur = types.SimpleNamespace(filter_channels_dp=256, kernel_size=3, p_dropout=0.1)
+    for n_spks in (1, 109):
+        theirs = ref.MatchaTTS(178, n_spks, 64, enc, dec, {"solver": "euler", "sigma_min": 1e-4}, dur)
+        mine = MatchaTTS(178, n_spks, 64, enc, dec, {"solver": "euler", "sigma_min": 1e-4}, dur)
+        a = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+        assert a == b
+        ckpt = {"state_dict": {"model." + k: v for k, v in theirs.state_dict().items()}}
+        load_lightning_checkpoint(mine, ckpt)                                  # strict
+        for k, v in theirs.state_dict().items():
+            assert torch.equal(mine.state_dict()[k], v), k
