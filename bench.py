@@ -258,6 +258,73 @@ def workload_config(args, extra=None):
     return c
 
 
+def run_synthesize(dev, B, n_timesteps, steps, world):
+    """tokens -> mel through the reference's own entry point (model.py:1264-1300) on the native modules: B utterances of 86
+    tokens, random-init weights with the duration head biased to ~4 frames per token (a random head gives ~1), so the batch
+    decodes ~B x 344 frames like configs[1].  One call at a time (synthesize reads y_lengths.max() on the host, :1281)."""
+    import math
+    import types
+    import torch
+    import torch.distributed as dist
+    from matcha_tts_b200 import MatchaTTS
+    enc_p = types.SimpleNamespace(encoder_type="RoPE Encoder", n_feats=80, n_channels=192, filter_channels=768, n_heads=2, n_layers=6,
+                                  kernel_size=3, p_dropout=0.1, prenet=True)
+    dec_p = types.SimpleNamespace(channels=(256, 256), dropout=0.05, attention_head_dim=64, n_blocks=1, num_mid_blocks=2, num_heads=2,
+                                  act_fn="snakebeta")
+    dur_p = types.SimpleNamespace(filter_channels_dp=256, kernel_size=3, p_dropout=0.1)
+    torch.manual_seed(0)
+    m = MatchaTTS(178, 1, 64, enc_p, dec_p, {"solver": "euler", "sigma_min": 1e-4}, dur_p).to(dev)
+    with torch.no_grad():
+        m.encoder.proj_w.proj.bias.fill_(math.log(3.5))
+    Tx = 86
+    g = torch.Generator().manual_seed(7)
+    tok_h = torch.randint(0, 178, (B, Tx), generator=g).pin_memory()
+    len_h = torch.full((B,), Tx, dtype=torch.long).pin_memory()
+    stream = torch.cuda.Stream(dev)
+    out_h = None
+    frames = 0
+    enc_ms = 0.0
+    with torch.cuda.stream(stream):
+        def once():
+            nonlocal out_h
+            tok = tok_h.to(dev, non_blocking=True)
+            lens = len_h.to(dev, non_blocking=True)
+            mel, ylen, _ = m.synthesise(tok, lens, n_timesteps=n_timesteps, temperature=0.667)
+            if out_h is None or out_h.shape != mel.shape:
+                out_h = torch.empty(mel.shape, dtype=mel.dtype).pin_memory()
+            out_h.copy_(mel, non_blocking=True)
+            yl = ylen.to("cpu", non_blocking=True)
+            stream.synchronize()
+            return int(yl.sum())
+        for _ in range(3):
+            once()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            frames += once()
+        dt = time.perf_counter() - t0
+        # the text encoder's share: CUDA events around its call alone
+        tok, lens = tok_h.to(dev), len_h.to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            m.encoder(tok, lens)
+        e1.record(stream)
+        e1.synchronize()
+        enc_ms = e0.elapsed_time(e1) / 10
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": world * frames / dt, "unit": "valid mel-frames/s", "ms_per_call": dt / steps * 1e3, "calls": steps, "batch": B,
+            "tokens_per_utterance": Tx, "mel_frames_per_call": frames // steps, "text_encoder_ms": enc_ms,
+            "text_encoder_launches": m.encoder.last_launch_count(),
+            "h2d_bytes_per_call": tok_h.numel() * 8 + len_h.numel() * 8, "d2h_bytes_per_call": out_h.numel() * 4,
+            "api": "MatchaTTS.synthesise(x, x_lengths, n_timesteps, temperature): native text encoder + duration predictor, alignment glue in "
+                   "torch (one host read of y_lengths.max()), native CFM decoder; pinned-host tokens in, mels out, one call at a time"}
+
+
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
@@ -552,6 +619,15 @@ def run_native(args):
         except Exception as exc:                                   # never take the headline line down
             config5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the whole reference call: MatchaTTS.synthesise(tokens, lengths, n_timesteps, temperature) -- native text encoder +
+    #      duration predictor, alignment glue, native decoder -- tokens in pinned host memory, mels read back to the host ----
+    synth = None
+    if not args.no_synthesize:
+        try:
+            synth = run_synthesize(dev, B, n, max(5, args.steps // 2), world)
+        except Exception as exc:
+            synth = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     ref_gpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         ref_gpu = reference_on_gpu(B, T, n, dev)
@@ -576,7 +652,7 @@ def run_native(args):
                 "sustained": sustained,
                 "serial": {"value": serial_value, "ms_per_step": serial_ms / args.steps, "ms_min": min(ms), "ms_max": max(ms),
                            "note": "one solve at a time (latency of a batch-64 solve), L2 flushed between steps"}}),
-            "roofline": roof, "cpu_baseline": cpu, "config5": config5, "reference_on_gpu": ref_gpu,
+            "roofline": roof, "cpu_baseline": cpu, "config5": config5, "synthesize": synth, "reference_on_gpu": ref_gpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": mu_h.numel() * 4 + mask_h.numel() * 4,
                     "d2h_bytes_per_step": out_h[0].numel() * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "CFM.forward(mu, mask, n_timesteps, temperature) per step, pinned-host mu/mask in and mel out per step; "
@@ -602,6 +678,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "3")), help="independent solves (batches) in flight at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=120, help="extra timed region of this many steps (0 = skip)")
+    ap.add_argument("--no-synthesize", action="store_true", help="skip the tokens -> mel leg (MatchaTTS.synthesise)")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 job folded into the line")
     ap.add_argument("--config5-utts", type=int, default=4096)
     ap.add_argument("--config5-frames", type=int, default=64 * 344, help="padded-frame budget per bucket")

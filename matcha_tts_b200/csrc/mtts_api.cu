@@ -971,7 +971,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   MttsHandle* h = new MttsHandle();
   h->cfg = *cfg;
   h->device = device;
-  h->cinp = (int)align_up(cfg->in_channels, 128);  // whole 128-column K pairs for the 3-D TMA boxes
+  h->cinp = (int)align_up(cfg->in_channels, 64);   // whole 64-column K chunks: 160 -> 192 (three chunks per tap, not four), 224 -> 256
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
