@@ -1,6 +1,10 @@
 // Masked self-attention of BasicTransformerBlock (reference model.py:670-705), 2 heads x 64.
 //
-// One CTA per (128-query tile, head, utterance), two CTAs per SM.
+// Work item = (128-query tile, head, utterance); persistent CTAs, two per SM, walk the items (item = blockIdx.x + k *
+// gridDim.x): tensor memory, barriers and descriptors are set up once per CTA, and the Q / K tile of the NEXT item is
+// requested as soon as the last Q K^T of the current one has completed (its V tile as soon as the last P V has), so the
+// loads of an item overlap the softmax / P V / normalisation of its predecessor (measured: 57.9 -> 55.7 us at level T,
+// B = 256 -- the second CTA of the SM already hid most of it; profiles/r02r_launch_table_B256_T344.txt).
 //   * key/value tiles are up to 192 keys wide (KT = the utterance's frames split evenly, a multiple of 16): T/2-level
 //     utterances (172 frames at T=344) need ONE tile -- plain softmax, no online rescaling -- and level-T ones two;
 //   * V stays row-major [rows][64] like K: the P V product reads it as an MN-major B operand (instruction-descriptor
@@ -45,6 +49,7 @@ struct Attn2Params {
   const __half* v;       // [rows][128] (quirk path)
   __half* out;           // [rows][128]
   int pdl_late;          // 1: release the dependent launch after the key/value loop instead of at entry
+  int B;                 // utterances (items = B * 2 heads * ceil(L / 128) query tiles)
 };
 
 // instruction descriptor with an MN-major B operand (V: keys x dims, dims contiguous)
@@ -115,9 +120,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int qd = warp & 3;     // TMEM lane quarter
   const int hf = warp >> 2;    // column half
   const int r = qd * 32 + lane;  // tile row of this thread
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int rowbase = b * p.Lp;
-  const int my_t = q0 + r;     // query frame handled by this thread (together with thread tid ^ 128)
 
   if (tid == 0) {
     mbar_init(bar_k, 1);
@@ -130,64 +132,32 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmV);
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
-  // written by the solve's prologue, several launches back: complete before the predecessor of this launch could start,
-  // so the load may overlap the set-up instead of following the dependency wait
-  const int npad = p.npad[b];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  // ---------------- quirk path: utterance has masked keys -> uniform mean of V over them ----------
-  if (npad > 0) {
-    const int d = tid & 63, part = tid >> 6;
-    const __half* vp = p.v + (size_t)rowbase * 128 + h * 64 + d;
-    float acc = 0.f;
-    for (int t = part; t < p.L; t += 4)
-      if (p.rowmask[rowbase + t] == 0.f) acc += __half2float(vp[(size_t)t * 128]);
-    s_mean[part * 64 + d] = acc;
-    __syncthreads();
-    if (tid < 64) s_mean[tid] = ((s_mean[tid] + s_mean[64 + tid]) + (s_mean[128 + tid] + s_mean[192 + tid])) / (float)npad;
-    __syncthreads();
-    if (p.pdl_late) pdl_launch_dependents();
-    if (my_t < p.L) {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64 + hf * 32);
-      const float* sm = s_mean + hf * 32;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = make_uint4(pack_h2(sm[8 * j], sm[8 * j + 1]), pack_h2(sm[8 * j + 2], sm[8 * j + 3]),
-                            pack_h2(sm[8 * j + 4], sm[8 * j + 5]), pack_h2(sm[8 * j + 6], sm[8 * j + 7]));
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem_base);
-    return;
-  }
-
-  // ---------------- full path: softmax(Q K^T) V on tcgen05 ------------------------------------------
   const uint32_t tS = tmem_base;                  // KT columns (<= 192)
   const uint32_t tO = tmem_base + ATT2_KT_MAX;    // 64 columns
   const uint32_t lane_off = uint32_t(qd * 32) << 16;
   const int KT = p.KT, nkv = p.nkv;
   const uint32_t kv_bytes = (uint32_t)KT * 128u;
-
-  auto issue_k = [&](int j) {   // one elected lane of warp 0
+  const int nqt = (p.L + 127) >> 7;
+  const int nitems = p.B * 2 * nqt;
+  // item -> (query tile fastest, then head, then utterance): a CTA's neighbours in the grid read the same K / V from L2
+  auto item_b = [&](int it) { return it / (2 * nqt); };
+  auto issue_k = [&](int it, int j) {   // one elected lane of warp 0; tile 0 brings the item's Q along
+    const int b = item_b(it), rem = it - b * 2 * nqt, h = rem / nqt, q0 = (rem - h * nqt) * 128;
     mbar_arrive_expect_tx(bar_k, kv_bytes + (j == 0 ? 16384u : 0u));
-    if (j == 0) tma_load_2d(sQ, &tmQ, bar_k, h * 64, rowbase + q0);
-    tma_load_2d(sK, &tmK, bar_k, h * 64, rowbase + j * KT);
+    if (j == 0) tma_load_2d(sQ, &tmQ, bar_k, h * 64, b * p.Lp + q0);
+    tma_load_2d(sK, &tmK, bar_k, h * 64, b * p.Lp + j * KT);
   };
-  auto issue_v = [&](int j) {
+  auto issue_v = [&](int it, int j) {
+    const int b = item_b(it), rem = it - b * 2 * nqt, h = rem / nqt;
     mbar_arrive_expect_tx(bar_v, kv_bytes);
-    tma_load_2d(sV, &tmV, bar_v, h * 64, rowbase + j * KT);
+    tma_load_2d(sV, &tmV, bar_v, h * 64, b * p.Lp + j * KT);
   };
-  if (warp == 0) {  // converged warp, one elected lane issues (uniform operands)
-    if (elect_one()) {
-      issue_k(0);
-      issue_v(0);
-    }
-    __syncwarp();
-  }
 
   const uint32_t idesc_s = umma_idesc_f16(128, (uint32_t)KT);
   constexpr uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
@@ -197,139 +167,197 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int cb = hf ? c0 : 0;
   const int nc = hf ? KT - c0 : c0;
   const int n32 = nc >> 5, rem16 = (nc >> 4) & 1;
-  const bool wvalid = q0 + qd * 32 < p.L;   // warp-uniform: at least one query row of this warp exists
-  float m_run = -INFINITY, l_run = 0.f;     // l_run: partial row sum over this thread's columns
-  float acc[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 
-  for (int j = 0; j < nkv; ++j) {
-    if (warp == 0) {
-      mbar_wait(bar_k, j & 1);
-      tc_fence_after();
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t dk = umma_desc_sw128(smem_u32(sK));
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
-    }
-    mbar_wait(bar_s, j & 1);
-    tc_fence_after();
-    if (warp == 0 && j + 1 < nkv) {  // K is free: fetch the next tile while this one goes through the softmax
-      if (elect_one()) issue_k(j + 1);
-      __syncwarp();
-    }
-
-    // ---- softmax over this tile's keys (keys >= L are excluded) ----
-    const int kvalid = min(KT, p.L - j * KT) - cb;   // valid keys among this thread's columns (may be <= 0)
-    const uint32_t ts = tS + lane_off + cb;
-    float mx = -INFINITY;
-    if (wvalid) {
+  uint32_t n_use = 0;        // key / value tiles processed so far: parity of the four barriers
+  bool pre = false;          // the first tiles of the current item were requested while the previous item ran
 #pragma unroll 1
-      for (int c = 0; c < n32; ++c) {
-        float s[32];
-        tmem_ld32(ts + c * 32, s);
-        tmem_ld_wait();
-        const int lim = kvalid - c * 32;
-        if (lim >= 32) mx = att3_chunk_max<32, false>(s, lim, mx);
-        else mx = att3_chunk_max<32, true>(s, lim, mx);
-      }
-      if (rem16) {
-        float s[16];
-        tmem_ld16(ts + n32 * 32, s);
-        tmem_ld_wait();
-        const int lim = kvalid - n32 * 32;
-        if (lim >= 16) mx = att3_chunk_max<16, false>(s, lim, mx);
-        else mx = att3_chunk_max<16, true>(s, lim, mx);
-      }
-    }
-    // row maximum over both column halves (half 0 always holds a valid key: its columns start at key 0 of the tile)
-    if (hf == 0) s_mx[r] = mx;
-    __syncthreads();
-    if (hf == 1) { mx = fmaxf(mx, s_mx[r]); s_mx[r] = mx; }
-    __syncthreads();
-    if (hf == 0) mx = s_mx[r];
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f((m_run - m_new) * LOG2E);
-    const float mb = m_new * LOG2E;
-    float rsum = 0.f;
-    if (wvalid) {
-      const int rx = r & 7;
-#pragma unroll 1
-      for (int c = 0; c < n32; ++c) {
-        float s[32];
-        tmem_ld32(ts + c * 32, s);
-        tmem_ld_wait();
-        const int gc = (cb >> 5) + c;  // 32-column chunk of the tile -> K-chunk gc/2 of P, 16-byte units (gc%2)*4.. of the 128-byte row
-        uint8_t* prow = sP + (gc >> 1) * 16384 + r * 128;
-        const int lim = kvalid - c * 32;
-        if (lim >= 32) rsum += att3_chunk_exp<32, false>(s, lim, mb, prow, (gc & 1) * 4, rx);
-        else rsum += att3_chunk_exp<32, true>(s, lim, mb, prow, (gc & 1) * 4, rx);
-      }
-      if (rem16) {
-        float s[16];
-        tmem_ld16(ts + n32 * 32, s);
-        tmem_ld_wait();
-        const int gc = (cb >> 5) + n32;
-        uint8_t* prow = sP + (gc >> 1) * 16384 + r * 128;
-        const int lim = kvalid - n32 * 32;
-        if (lim >= 16) rsum += att3_chunk_exp<16, false>(s, lim, mb, prow, (gc & 1) * 4, rx);
-        else rsum += att3_chunk_exp<16, true>(s, lim, mb, prow, (gc & 1) * 4, rx);
-      }
-    }
-    l_run = l_run * alpha + rsum;
-    m_run = m_new;
-    if (j > 0) {
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int b = item_b(it), rem = it - b * 2 * nqt, h = rem / nqt, q0 = (rem - h * nqt) * 128;
+    const int rowbase = b * p.Lp;
+    const int my_t = q0 + r;     // query frame handled by this thread (together with thread tid ^ 128)
+    const int nxt = it + (int)gridDim.x;
+    const bool last_item = nxt >= nitems;
+    // written by the solve's prologue, several launches back
+    const int npad = p.npad[b];
+    const bool nxt_full = !last_item && p.npad[item_b(nxt)] == 0;
+
+    // ---------------- quirk path: utterance has masked keys -> uniform mean of V over them ----------
+    if (npad > 0) {
+      const int d = tid & 63, part = tid >> 6;
+      const __half* vp = p.v + (size_t)rowbase * 128 + h * 64 + d;
+      float acc = 0.f;
+      for (int t = part; t < p.L; t += 4)
+        if (p.rowmask[rowbase + t] == 0.f) acc += __half2float(vp[(size_t)t * 128]);
+      __syncthreads();   // the previous item's readers of the P region are done
+      s_mean[part * 64 + d] = acc;
+      __syncthreads();
+      if (tid < 64) s_mean[tid] = ((s_mean[tid] + s_mean[64 + tid]) + (s_mean[128 + tid] + s_mean[192 + tid])) / (float)npad;
+      __syncthreads();
+      if (last_item && p.pdl_late) pdl_launch_dependents();
+      if (my_t < p.L) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64 + hf * 32);
+        const float* sm = s_mean + hf * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] *= alpha;
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_h2(sm[8 * j], sm[8 * j + 1]), pack_h2(sm[8 * j + 2], sm[8 * j + 3]),
+                              pack_h2(sm[8 * j + 4], sm[8 * j + 5]), pack_h2(sm[8 * j + 6], sm[8 * j + 7]));
+      }
+      __syncthreads();   // s_mean is read before the next item reuses the region
+      pre = false;
+      continue;
     }
 
-    fence_proxy_async_smem();  // P written with generic-proxy stores, read by the tensor core
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      mbar_wait(bar_v, j & 1);
-      tc_fence_after();
-      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dv0 = umma_desc_sw128(smem_u32(sV));
-      const int ksteps = KT >> 4;
+    // ---------------- full path: softmax(Q K^T) V on tcgen05 ------------------------------------------
+    if (!pre && warp == 0) {  // converged warp, one elected lane issues (uniform operands)
       if (elect_one()) {
-        for (int k = 0; k < ksteps; ++k)   // P: K-major, 16 keys = 32 B inside the 128-byte row of K-chunk k/4;
-                                           // V: MN-major, 16 keys = 16 rows of 128 B = 2048 B (descriptor address in 16-byte units)
-          umma_f16(tO, dp0 + (k >> 2) * (16384 >> 4) + 2 * (k & 3), dv0 + k * (2048 >> 4), idesc_o, k != 0);
-        umma_commit(bar_o);
+        issue_k(it, 0);
+        issue_v(it, 0);
       }
       __syncwarp();
     }
-    mbar_wait(bar_o, j & 1);
-    tc_fence_after();
-    if (warp == 0 && j + 1 < nkv) {  // V (and P) are free
-      if (elect_one()) issue_v(j + 1);
+    const bool wvalid = q0 + qd * 32 < p.L;   // warp-uniform: at least one query row of this warp exists
+    float m_run = -INFINITY, l_run = 0.f;     // l_run: partial row sum over this thread's columns
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+
+    for (int j = 0; j < nkv; ++j, ++n_use) {
+      const uint32_t ph = n_use & 1;
+      if (warp == 0) {
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+        const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+        const uint64_t dk = umma_desc_sw128(smem_u32(sK));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      if (warp == 0) {  // K (and after the last tile Q) is free: fetch what comes next while this tile goes through the softmax
+        if (elect_one()) {
+          if (j + 1 < nkv) issue_k(it, j + 1);
+          else if (nxt_full) issue_k(nxt, 0);
+        }
+        __syncwarp();
+      }
+
+      // ---- softmax over this tile's keys (keys >= L are excluded) ----
+      const int kvalid = min(KT, p.L - j * KT) - cb;   // valid keys among this thread's columns (may be <= 0)
+      const uint32_t ts = tS + lane_off + cb;
+      float mx = -INFINITY;
+      if (wvalid) {
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          float s[32];
+          tmem_ld32(ts + c * 32, s);
+          tmem_ld_wait();
+          const int lim = kvalid - c * 32;
+          if (lim >= 32) mx = att3_chunk_max<32, false>(s, lim, mx);
+          else mx = att3_chunk_max<32, true>(s, lim, mx);
+        }
+        if (rem16) {
+          float s[16];
+          tmem_ld16(ts + n32 * 32, s);
+          tmem_ld_wait();
+          const int lim = kvalid - n32 * 32;
+          if (lim >= 16) mx = att3_chunk_max<16, false>(s, lim, mx);
+          else mx = att3_chunk_max<16, true>(s, lim, mx);
+        }
+      }
+      // row maximum over both column halves (half 0 always holds a valid key: its columns start at key 0 of the tile)
+      if (hf == 0) s_mx[r] = mx;
+      __syncthreads();
+      if (hf == 1) { mx = fmaxf(mx, s_mx[r]); s_mx[r] = mx; }
+      __syncthreads();
+      if (hf == 0) mx = s_mx[r];
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * LOG2E);
+      const float mb = m_new * LOG2E;
+      float rsum = 0.f;
+      if (wvalid) {
+        const int rx = r & 7;
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          float s[32];
+          tmem_ld32(ts + c * 32, s);
+          tmem_ld_wait();
+          const int gc = (cb >> 5) + c;  // 32-column chunk of the tile -> K-chunk gc/2 of P, 16-byte units (gc%2)*4.. of the 128-byte row
+          uint8_t* prow = sP + (gc >> 1) * 16384 + r * 128;
+          const int lim = kvalid - c * 32;
+          if (lim >= 32) rsum += att3_chunk_exp<32, false>(s, lim, mb, prow, (gc & 1) * 4, rx);
+          else rsum += att3_chunk_exp<32, true>(s, lim, mb, prow, (gc & 1) * 4, rx);
+        }
+        if (rem16) {
+          float s[16];
+          tmem_ld16(ts + n32 * 32, s);
+          tmem_ld_wait();
+          const int gc = (cb >> 5) + n32;
+          uint8_t* prow = sP + (gc >> 1) * 16384 + r * 128;
+          const int lim = kvalid - n32 * 32;
+          if (lim >= 16) rsum += att3_chunk_exp<16, false>(s, lim, mb, prow, (gc & 1) * 4, rx);
+          else rsum += att3_chunk_exp<16, true>(s, lim, mb, prow, (gc & 1) * 4, rx);
+        }
+      }
+      l_run = l_run * alpha + rsum;
+      m_run = m_new;
+      if (j > 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] *= alpha;
+      }
+
+      fence_proxy_async_smem();  // P written with generic-proxy stores, read by the tensor core
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dv0 = umma_desc_sw128(smem_u32(sV));
+        const int ksteps = KT >> 4;
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)   // P: K-major, 16 keys = 32 B inside the 128-byte row of K-chunk k/4;
+                                             // V: MN-major, 16 keys = 16 rows of 128 B = 2048 B (descriptor address in 16-byte units)
+            umma_f16(tO, dp0 + (k >> 2) * (16384 >> 4) + 2 * (k & 3), dv0 + k * (2048 >> 4), idesc_o, k != 0);
+          umma_commit(bar_o);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      if (warp == 0) {  // V (and P) are free
+        if (elect_one()) {
+          if (j + 1 < nkv) issue_v(it, j + 1);
+          else if (nxt_full) issue_v(nxt, 0);
+        }
+        __syncwarp();
+      }
+      if (wvalid) {
+        float o[32];
+        tmem_ld32(tO + lane_off + hf * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += o[i];
+      }
+      tc_fence_before();
       __syncwarp();
     }
-    if (wvalid) {
-      float o[32];
-      tmem_ld32(tO + lane_off + hf * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] += o[i];
-    }
-    tc_fence_before();
-    __syncwarp();
-  }
+    pre = nxt_full;
 
-  if (p.pdl_late) pdl_launch_dependents();
-  s_l[hf * 128 + r] = l_run;   // P is idle: every P V product has completed
-  __syncthreads();
-  if (my_t < p.L) {
-    const float inv = 1.f / (s_l[r] + s_l[128 + r]);   // fixed order: both threads of the row use the same sum
-    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64 + hf * 32);
+    if (last_item && p.pdl_late) pdl_launch_dependents();
+    s_l[hf * 128 + r] = l_run;   // P is idle: every P V product has completed
+    __syncthreads();
+    if (my_t < p.L) {
+      const float inv = 1.f / (s_l[r] + s_l[128 + r]);   // fixed order: both threads of the row use the same sum
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(rowbase + my_t) * 128 + h * 64 + hf * 32);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      dst[j] = make_uint4(pack_h2(acc[8 * j] * inv, acc[8 * j + 1] * inv), pack_h2(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv),
-                          pack_h2(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv), pack_h2(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv));
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_h2(acc[8 * j] * inv, acc[8 * j + 1] * inv), pack_h2(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv),
+                            pack_h2(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv), pack_h2(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv));
+    }
+    // the next item's softmax writes P only after two more block barriers (row-maximum exchange): s_l has been read by then
   }
   tc_fence_before();
   __syncthreads();

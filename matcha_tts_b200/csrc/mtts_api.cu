@@ -732,8 +732,10 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
   }
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
-    dim3 grid((lc.L + 127) / 128, 2, w.B);
+    const int items = ((lc.L + 127) / 128) * 2 * w.B;
+    dim3 grid(items < 2 * h->num_sms ? items : 2 * h->num_sms);   // persistent: two CTAs per SM walk the (query tile, head, utterance) items
     Attn2Params ap{};
+    ap.B = w.B;
     ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
     ap.v = H(w.v); ap.out = H(w.o); ap.pdl_late = h->pdl_late ? 1 : 0;
     CUDA_TRY(launch_k(h, attention3_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, stream, lm.q, lm.k2, lm.v2, ap));
