@@ -180,8 +180,11 @@ int mtts_text_load_weight(MttsTextHandle* h, int idx, const float* dev_src, int6
 int mtts_text_weights_loaded(const MttsTextHandle* h);
 size_t mtts_text_workspace_bytes(const MttsTextHandle* h, int B, int T_x);
 int mtts_text_release_workspace(MttsTextHandle* h, const void* workspace, size_t workspace_bytes);
+/* use_graph != 0 captures the call's ~57 launches into a CUDA graph (cached per pointers / shape; the stream must be
+ * capturable, i.e. not the legacy default stream) */
 int mtts_text_encoder_forward(MttsTextHandle* h, const int64_t* tokens, const int64_t* lengths, const float* spks, float* mu,
-                              float* logw, float* x_mask, void* workspace, size_t workspace_bytes, int B, int T_x, void* stream);
+                              float* logw, float* x_mask, void* workspace, size_t workspace_bytes, int B, int T_x, int use_graph,
+                              void* stream);
 int mtts_text_last_launch_count(const MttsTextHandle* h);
 /* introspection used by the parity tests: stop after n kernel launches (n < 0: run everything); byte offset of a named
  * intermediate ("X", "X1", "Y", "H", "O", "QKV", "F": fp16 rows of 256 / 768 / filter_channels columns, T_x + 2 rows per

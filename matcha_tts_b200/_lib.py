@@ -72,7 +72,8 @@ SIGNATURES = {
     "mtts_text_weights_loaded": (C.c_int, [C.c_void_p]),
     "mtts_text_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "mtts_text_release_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
-    "mtts_text_encoder_forward": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+    "mtts_text_encoder_forward": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p]),
     "mtts_text_last_launch_count": (C.c_int, [C.c_void_p]),
     "mtts_text_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "mtts_text_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),

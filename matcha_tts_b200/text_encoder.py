@@ -86,7 +86,10 @@ class _TextEngine:
         with torch.cuda.device(device):
             self.arena, self.arena_ptr = _aligned_buffer(self.lib.mtts_text_weight_arena_bytes(h), device, 256)
         self.ws: Dict[Tuple[int, int], Tuple[torch.Tensor, int, int]] = {}
+        self.static: Dict[Tuple[int, int], dict] = {}
+        self.side_stream = None
         self.packed_version = None
+        self.n_feats = cfg.n_feats
 
     def __del__(self):
         try:
@@ -107,7 +110,8 @@ class _TextEngine:
             keep.append(src)
             _lib.check(self.lib.mtts_text_load_weight(self.h, i, src.data_ptr(), src.numel(), st))
         torch.cuda.current_stream(self.device).synchronize()   # `keep` may be freed afterwards
-        self.ws.clear()                                        # set_weight_arena dropped the plans
+        self.ws.clear()                                        # set_weight_arena dropped the plans and graphs
+        self.static.clear()
 
     def workspace(self, B: int, Tx: int):
         key = (B, Tx)
@@ -120,18 +124,54 @@ class _TextEngine:
                 buf, ptr, nb = self.ws.pop(old)
                 torch.cuda.synchronize(self.device)
                 _lib.check(self.lib.mtts_text_release_workspace(self.h, ptr, nb))
+                self.static.pop(old, None)
             buf, ptr = _aligned_buffer(n, self.device, 1024)
             self.ws[key] = (buf, ptr, n)
         else:
             self.ws[key] = self.ws.pop(key)
         return self.ws[key]
 
-    def forward(self, tokens, lengths, spks, mu, logw, x_mask):
+    def forward(self, tokens, lengths, spks, use_graph: bool = True):
+        """-> (mu, logw, x_mask).  With use_graph the inputs are staged into per-shape static buffers and the call's launches
+        replay as one CUDA graph (keyed on pointers inside the library); the outputs are fresh tensors either way."""
         B, Tx = tokens.shape
         _, ptr, n = self.workspace(B, Tx)
+        dev = tokens.device
+        if not use_graph:
+            mu = torch.empty(B, self.n_feats, Tx, dtype=torch.float32, device=dev)
+            logw = torch.empty(B, 1, Tx, dtype=torch.float32, device=dev)
+            x_mask = torch.empty(B, 1, Tx, dtype=torch.float32, device=dev)
+            _lib.check(self.lib.mtts_text_encoder_forward(
+                self.h, tokens.data_ptr(), lengths.data_ptr(), spks.data_ptr() if spks is not None else None, mu.data_ptr(),
+                logw.data_ptr(), x_mask.data_ptr(), ptr, n, B, Tx, 0, self._stream()))
+            return mu, logw, x_mask
+        key = (B, Tx)
+        st = self.static.get(key)
+        if st is None:
+            with torch.inference_mode(False):
+                st = {"tok": torch.empty(B, Tx, dtype=torch.int64, device=dev), "len": torch.empty(B, dtype=torch.int64, device=dev),
+                      "spk": None if spks is None else torch.empty(spks.shape, dtype=torch.float32, device=dev),
+                      "mu": torch.empty(B, self.n_feats, Tx, dtype=torch.float32, device=dev),
+                      "logw": torch.empty(B, 1, Tx, dtype=torch.float32, device=dev),
+                      "mask": torch.empty(B, 1, Tx, dtype=torch.float32, device=dev)}
+            self.static[key] = st
+        st["tok"].copy_(tokens); st["len"].copy_(lengths)
+        if spks is not None:
+            st["spk"].copy_(spks)
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0:                 # the legacy default stream cannot be captured
+            if self.side_stream is None:
+                self.side_stream = torch.cuda.Stream(self.device)
+            self.side_stream.wait_stream(cur)
+            run = self.side_stream
+        else:
+            run = cur
         _lib.check(self.lib.mtts_text_encoder_forward(
-            self.h, tokens.data_ptr(), lengths.data_ptr(), spks.data_ptr() if spks is not None else None, mu.data_ptr(),
-            logw.data_ptr(), x_mask.data_ptr(), ptr, n, B, Tx, self._stream()))
+            self.h, st["tok"].data_ptr(), st["len"].data_ptr(), st["spk"].data_ptr() if spks is not None else None, st["mu"].data_ptr(),
+            st["logw"].data_ptr(), st["mask"].data_ptr(), ptr, n, B, Tx, 1, run.cuda_stream))
+        if run is not cur:
+            cur.wait_stream(run)
+        return st["mu"].clone(), st["logw"].clone(), st["mask"].clone()
 
     def launch_count(self) -> int:
         return self.lib.mtts_text_last_launch_count(self.h)
@@ -173,6 +213,7 @@ class TextEncoder(nn.Module):
                 node = node._modules[part]
             node.register_parameter(leaf, nn.Parameter(v, requires_grad=False))
         self._engines: Dict[torch.device, _TextEngine] = {}
+        self.use_cuda_graph = True
 
     def _weights_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -210,10 +251,7 @@ class TextEncoder(nn.Module):
         tok = x.detach().to(torch.int64).contiguous()
         lens = x_lengths.detach().to(device=x.device, dtype=torch.int64).contiguous()
         s32 = None if spks is None else spks.detach().to(device=x.device, dtype=torch.float32).contiguous()
-        mu = torch.empty(B, self.n_feats, Tx, dtype=torch.float32, device=x.device)
-        logw = torch.empty(B, 1, Tx, dtype=torch.float32, device=x.device)
-        x_mask = torch.empty(B, 1, Tx, dtype=torch.float32, device=x.device)
-        eng.forward(tok, lens, s32, mu, logw, x_mask)
+        mu, logw, x_mask = eng.forward(tok, lens, s32, use_graph=self.use_cuda_graph)
         return mu, logw, x_mask
 
     def last_launch_count(self) -> int:
