@@ -57,7 +57,6 @@ struct TailParams {
   __half* out;           // [rows, 256]
   int w_hint;            // 1: weight pieces are loaded with the L2 evict_last policy
   int pdl_late;          // 1: griddepcontrol.launch_dependents at the last tile's final epilogue instead of at entry
-  int sleep_wait;        // 1: the weight producer warp sleeps between polls of its ring slots instead of spinning
   long long* tl;         // debug timeline [gridDim.x][128] clock64 stamps of the first tile (null in production)
 };
 
@@ -157,7 +156,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       constexpr uint32_t WBYTES = TAIL_PIECE / CG;   // this CTA's share of a weight piece
       auto slot_acquire = [&]() -> uint32_t {
         const uint32_t slot = it % TAIL_NST, use = it / TAIL_NST;
-        mbar_wait_opt(&empty_bar[slot], (use & 1) ^ 1, p.sleep_wait);
+        mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
         ++it;
         return slot;
       };

@@ -106,8 +106,6 @@ struct GemmParams {
                    //    all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu); the res_conv pass
                    //    stages the tiles once more and reads them one row in
   int relu;        // EPI_PLAIN: 1 = ReLU after bias (+ residual), before the row mask (text encoder FFN / duration predictor convs)
-  int sleep_wait;  // 1: the TMA producer warps sleep between polls of their ring slots instead of spinning (the polls compete with
-                   //    the epilogue warps of their scheduler partitions for issue slots)
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -294,7 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int q = 0; q < nsrc; ++q) CH += p.seg[q].nchunks;
       const bool has_res = p.res_chunk0 > 0;
       auto put = [&](int kc, int n0) {
-        mbar_wait_opt(&empty_bar[stage], phase ^ 1, p.sleep_wait);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sb = smem + TAP_B_OFF + stage * TAP_B_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
@@ -316,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int n0 = (tile % p.n_tiles) * BN;
       for (int kc = 0; kc < total_chunks; kc += KSUB) {
-        mbar_wait_opt(&empty_bar[stage], phase ^ 1, p.sleep_wait);   // converged warp; one elected lane issues
+        mbar_wait(&empty_bar[stage], phase ^ 1);   // converged warp; one elected lane issues
         if (elect_one()) {
           uint8_t* sb = smem + stage * SM::STAGE_BYTES + SM::A_BYTES;
           if constexpr (CG == 2) {   // this CTA's half of the weight tile; bytes are counted on the leader's barrier
@@ -372,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const GemmSeg sg = p.seg[q];
             const CUtensorMap* tm = q ? &tmA1 : &tmA0;
             for (int c = 0; c < sg.nchunks; ++c) {
-              mbar_wait_opt(&aempty[stage], phase ^ 1, p.sleep_wait);
+              mbar_wait(&aempty[stage], phase ^ 1);
               if (elect_one()) {
                 mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
                 tma_load_2d(smem + stage * TAP_A_BYTES, tm, &afull[stage], sg.col0 + c * GEMM_BK, r0 - 1);
@@ -390,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const GemmSeg sg = p.seg[s];
         const CUtensorMap* tm = sg.src ? &tmA1 : &tmA0;
         for (int c = 0; c < sg.nchunks; c += KSUB) {
-          mbar_wait_opt(&empty_bar[stage], phase ^ 1, p.sleep_wait);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             if constexpr (CG == 2) {
               const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);

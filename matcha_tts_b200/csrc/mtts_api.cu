@@ -224,13 +224,12 @@ struct MttsHandle {
                             // measured equal at full occupancy (70 vs 73 us at level T, 46 vs 45 us at level T/2, B=256) and slower for one
                             // solve at a time (3.55 vs 3.75 M frames/s): its transform runs on 8 warps per SM at ~0.4 IPC per scheduler
                             // partition while the stand-alone pass has ~40 warps per SM -- profiles/r02_gnbqkv_*.txt
-  bool sleep_wait = false;  // MTTS_SLEEPWAIT=1: TMA producer warps sleep between polls of their ring slots
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
   bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
                           // pair launches measured -1% (4.57 vs 4.63 M frames/s) although the kernel alone gains 5-10% at full occupancy
-  bool pdl_late = true;  // MTTS_PDL_EARLY=1 restores griddepcontrol.launch_dependents at kernel entry.  Default: GEMM / tail / attention
-                         // CTAs release their dependents when their last accumulator is complete: dependents released at entry sit
+  bool pdl_late = true;  // GEMM / tail / attention CTAs release their dependents (griddepcontrol.launch_dependents) when their last
+                         // accumulator is complete, not at kernel entry: dependents released at entry sit
                          // on SM slots (shared memory, TMEM) that ready kernels of another chain / solve could use (+4.5% with three
                          // solves in flight, +3% with one)
   // utterance sub-batches ("chains") of one solve run on forked streams so that their kernels overlap:
@@ -568,7 +567,6 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   pp.w_hint = h->w_hint ? 1 : 0;
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
   pp.pdl_late = h->pdl_late ? 1 : 0;
-  pp.sleep_wait = h->sleep_wait ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
                     wmap, pp));
@@ -598,7 +596,6 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
         GemmParams pp = p;
         pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
         pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
-        pp.sleep_wait = h->sleep_wait ? 1 : 0;
         CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
                                stream, a0.d2, a1.d2, wmap.d2h, pp));
         launched(h);
@@ -747,7 +744,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     tp.M = lc.rows; tp.xr = H(w.xr); tp.b_o = F(sw.o_b); tp.ln_g = F(sw.ln3_g); tp.ln_b = F(sw.ln3_b);
     tp.b1 = F(sw.ff1_b); tp.sn_a = F(sw.sn_a); tp.sn_ib = F(sw.sn_ib); tp.b2 = F(sw.ff2_b);
     tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
-    tp.tl = h->tail_tl; tp.sleep_wait = h->sleep_wait ? 1 : 0;
+    tp.tl = h->tail_tl;
     const int tiles = (lc.rows + 127) / 128;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     if (h->tail_pairs) {
@@ -977,14 +974,12 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->nspk = cfg->in_channels - 2 * cfg->out_channels;
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
-  if (const char* e = getenv("MTTS_PDL_EARLY")) h->pdl_late = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIRS")) h->cta_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
-  if (const char* e = getenv("MTTS_SLEEPWAIT")) h->sleep_wait = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {

@@ -58,18 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same for a warp that waits LONG next to warps that compute (a producer / MMA-issuer warp beside worker warps on its
 // scheduler partition): a failed try_wait returns after ~80 cycles, so the plain spin above issues ~5 instructions every
 // 80 cycles -- a fifth of all instructions gnb_qkv_kernel executed were spin instructions on two of the four partitions
-// (profiles/r02f_ncu_gnbqkv.txt).  Sleeping between polls gives the slots back; the wake-up costs <= ~0.1 us.
+// (profiles/r02_gnbqkv_ncu_summary.txt).  Sleeping between polls gives the slots back; the wake-up costs <= ~0.1 us.  (In
+// the conv / tail kernels, whose epilogue warps are not issue-bound, it changed nothing: profiles/r02m_*.)
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(96);
     if (++spins > (1u << 24)) { __trap(); }
   }
-}
-
-__device__ __forceinline__ void mbar_wait_opt(uint64_t* bar, uint32_t parity, int sleep) {
-  if (sleep) mbar_wait_sleep(bar, parity);
-  else mbar_wait(bar, parity);
 }
 
 // ------------------------------------------------------------------ CTA pairs (cluster of 2, tcgen05 cta_group::2)

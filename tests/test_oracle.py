@@ -100,6 +100,24 @@ def test_emulated_fp16_pipeline_within_tolerance(sds):
     assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
 
 
+def test_emulated_bf16_operands_miss_the_bar(sds):
+    """Why the GEMM operands are fp16 and not the north star's bf16 (same tcgen05 kind::f16 rate): the same emulation with
+    bf16 operands / storage -- fp32 accumulation, statistics and state, exactly the native pipeline's structure -- lands
+    ABOVE the 1e-3 relative-L2 bar (SURVEY.md section 7.3 item 1 measured 2.0-3.4e-3), fp16 well below it.  The bf16 figure
+    is printed so that it is reported next to the fp16 one."""
+    cfg, sd = O.DecoderCfg(), sds[160]
+    mu, mask, z0, _ = O.make_inputs(cfg, 2, 64, [64, 50], seed=4)
+    ref = O.euler_solve(sd, cfg, z0, mu, mask, 10)
+    out = {}
+    for name, dt in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+        z = O.euler_solve(sd, cfg, z0, mu, mask, 10, emu=O.Emu(operand=dt, conv_out=dt, attn=dt, resid=dt))
+        out[name] = O.parity_errors(z, ref, mask)
+    print(f"emulated 10-step error vs fp32: fp16 max-abs {out['fp16'][0]:.2e} rel-L2 {out['fp16'][1]:.2e}; "
+          f"bf16 max-abs {out['bf16'][0]:.2e} rel-L2 {out['bf16'][1]:.2e}")
+    assert out["fp16"][1] <= O.TOL_REL_L2 < out["bf16"][1], out
+    assert out["bf16"][1] >= 3 * out["fp16"][1]
+
+
 def test_helpers():
     assert O.fix_len_compatibility(343) == 344 and O.fix_len_compatibility(344) == 344
     m = O.sequence_mask(torch.tensor([2, 0, 3]), 3)
