@@ -19,6 +19,7 @@
 #include "ff_tail.cuh"
 #include "gemm_tc.cuh"
 #include "gnb_qkv.cuh"
+#include "qkv.cuh"
 
 using namespace mtts;
 
@@ -219,6 +220,8 @@ struct MttsHandle {
   bool w_hint = true;      // weights are loaded with the L2 evict_last hint
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
+  bool qkv_gemm = false;    // MTTS_QKV_GEMM=1: the QKV projection through the generic gemm_tc_kernel<128, EPI_QKV> (one unit per N tile,
+                            // the activation tile staged three times) instead of qkv_kernel (qkv.cuh)
   bool fused_gnb = false;   // MTTS_GNBQKV=1: gnb_qkv_kernel (GroupNorm-apply + residual + LayerNorm1 + QKV GEMM in one launch, 43 instead of 49
                             // launches per evaluation) instead of the GroupNorm-apply pass followed by the QKV GEMM launch.  Bit-identical;
                             // measured equal at full occupancy (70 vs 73 us at level T, 46 vs 45 us at level T/2, B=256) and slower for one
@@ -720,7 +723,17 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
   }
   // q | k | v
-  {
+  if (!h->qkv_gemm) {
+    if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
+      QkvParams qp{};
+      qp.M = lc.rows; qp.q = H(w.q); qp.k = H(w.k); qp.v = H(w.v); qp.w_hint = h->w_hint ? 1 : 0; qp.pdl_late = h->pdl_late ? 1 : 0;
+      qp.tl = h->tail_tl;   // debug stamps share the tail kernel's buffer (tools/qkv_timeline.py stops before the first tail launch)
+      const int tiles = (lc.rows + 127) / 128;
+      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+      CUDA_TRY(launch_k(h, qkv_kernel, dim3(grid), dim3(QKV_THREADS), QKV_SMEM, stream, lm.a.d2, sw.m_qkv.d2, qp));
+      launched(h);
+    }
+  } else {
     GemmParams p = base;
     segs_taps(p, 1, kTap1, C, 0);
     p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.v = H(w.v);
@@ -980,6 +993,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
+  if (const char* e = getenv("MTTS_QKV_GEMM")) h->qkv_gemm = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
@@ -1000,6 +1014,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>();
     e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
+    if (cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gnb_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;

@@ -446,7 +446,7 @@ def test_chains_setting_keeps_results(lj):
 # ---------------------------------------------------------------------------------------------
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV"])
+@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV", "MTTS_QKV_GEMM"])
 def test_opt_in_variants(env):
     old = os.environ.get(env)
     os.environ[env] = "1"
