@@ -316,8 +316,18 @@ class Decoder(nn.Module):
         return _lib.MttsConfig(self.in_channels, self.out_channels, self.channels[0], self.num_heads,
                                self.attention_head_dim, self.num_mid_blocks)
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .half() swap the parameters' storage without touching their version counters
+        self._storage_epoch = getattr(self, "_storage_epoch", 0) + 1
+        return super()._apply(fn, *args, **kwargs)
+
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Changes whenever a parameter is written in place (version counters: load_state_dict, copy_, optimiser steps) or
+        moved (storage epoch).  ~170 attribute reads per call instead of as many data_ptr() calls."""
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        return (getattr(self, "_storage_epoch", 0),) + tuple(p._version for p in plist)
 
     def _engine(self, device: torch.device) -> _Engine:
         if device.type != "cuda":

@@ -215,8 +215,15 @@ class TextEncoder(nn.Module):
         self._engines: Dict[torch.device, _TextEngine] = {}
         self.use_cuda_graph = True
 
+    def _apply(self, fn, *args, **kwargs):
+        self._storage_epoch = getattr(self, "_storage_epoch", 0) + 1      # .to() / .cuda() swap storage without bumping versions
+        return super()._apply(fn, *args, **kwargs)
+
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        return (getattr(self, "_storage_epoch", 0),) + tuple(p._version for p in plist)
 
     def _engine(self, device: torch.device) -> _TextEngine:
         if device.type != "cuda":
