@@ -83,6 +83,12 @@ def _worker(rank, world, port, lengths, ret):
     out = Bt.solve_sharded(mus, _stub_solver, spks=spks, max_frames=4096)
     if rank == 0:
         ret.update({i: v for i, v in out.items()})
+    # gather="rank0": only rank 0 holds the gathered mels; the lazy dict cuts its views on access
+    out0 = Bt.solve_sharded(mus, _stub_solver, spks=spks, max_frames=4096, gather="rank0")
+    ret[f"rank0_mode_len_{rank}"] = len(out0)
+    if rank == 0:
+        ret["rank0_mode_equal"] = all(torch.equal(out0[i], out[i]) for i in range(len(lengths))) and sorted(out0) == sorted(out)
+        ret["lazy_items"] = all(v.shape == (80, lengths[i]) for i, v in out0.items()) and len(out0.values()) == len(lengths)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -106,6 +112,8 @@ def test_two_rank_gloo_matches_single_process():
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, _free_port(), lengths, ret), nprocs=2, join=True)
         multi = dict(ret)
+    assert multi.pop("rank0_mode_len_0") == len(lengths) and multi.pop("rank0_mode_len_1") == 0
+    assert multi.pop("rank0_mode_equal") and multi.pop("lazy_items")
     assert sorted(multi) == sorted(single)
     for i in single:
         assert multi[i].shape == (80, lengths[i])
