@@ -695,6 +695,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b = row_ok ? p.rowb[row] : -1;
         const int t = row - b * p.Lp;
         const float m = (b >= 0) ? p.rowmask[row] : 0.f;
+        // the state z of this row's channels is requested BEFORE the accumulator wait (it does not depend on the MMAs): one
+        // memory round trip under the main loop instead of one per 32-channel chunk after it.  All state loads precede the
+        // first store (zout may alias zbase; every element is read and written by the same thread).
+        float zb[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = cbase + c * 32;
+          const int nj = min(32, p.n_valid - col0);  // warp-uniform
+          const size_t idx0 = ((size_t)max(b, 0) * p.n_valid + col0) * p.T + t;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) zb[c][j] = (b >= 0 && p.zbase != nullptr && j < nj) ? p.zbase[idx0 + (size_t)j * p.T] : 0.f;
+        }
         if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
         __syncwarp();
         tc_fence_after();
@@ -704,17 +716,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int col0 = cbase + c * 32;
           const int nj = min(32, p.n_valid - col0);  // warp-uniform
           if (nj > 0) {
-            float v[32], zb[32];
+            float v[32];
             tmem_ld32(taddr + c * 32, v);
             const size_t idx0 = ((size_t)max(b, 0) * p.n_valid + col0) * p.T + t;
-            // all state loads are issued before the first store (zout may alias zbase)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) zb[j] = (b >= 0 && p.zbase != nullptr && j < nj) ? p.zbase[idx0 + (size_t)j * p.T] : 0.f;
             tmem_ld_wait();
             if (b >= 0) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float o = fmaf(p.zscale, (v[j] + lds_f32(sp0 + (c * 32 + j) * 4)) * m, zb[j]);
+                const float o = fmaf(p.zscale, (v[j] + lds_f32(sp0 + (c * 32 + j) * 4)) * m, zb[c][j]);
                 v[j] = o;
               }
 #pragma unroll

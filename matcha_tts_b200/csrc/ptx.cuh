@@ -433,9 +433,10 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 // Mish(x) = x * tanh(softplus(x)), torch semantics (softplus threshold 20).
 // tanh(log(1+e)) = (e^2 + 2e) / (e^2 + 2e + 2)  -- one exp, one divide, no cancellation.
 __device__ __forceinline__ float mish_f(float x) {
-  // tanh(softplus(x)) = w / (w + 2), w = e (e + 2), e = exp(x):  x * (1 - 2 / (w + 2)).  Clamping x at 20 keeps e*e
-  // finite and reproduces torch's softplus threshold (the factor is 1 to fp32 precision beyond it).
-  const float e = __expf(fminf(x, 20.f));
+  // tanh(softplus(x)) = w / (w + 2), w = e (e + 2), e = exp(x):  x * (1 - 2 / (w + 2)).  No clamp is needed: beyond
+  // torch's softplus threshold (x > 20) the factor is 1 to fp32 precision, and when e or e*e overflows to +inf the
+  // reciprocal is 0 and the result is exactly x -- the same bits as with x clamped at 20, one FMNMX per element less.
+  const float e = __expf(x);
   const float t2 = fmaf(e, e + 2.f, 2.f);      // w + 2
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t2));
