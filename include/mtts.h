@@ -192,6 +192,58 @@ int mtts_text_last_launch_count(const MttsTextHandle* h);
 int mtts_text_debug_set_launch_limit(MttsTextHandle* h, int n);
 int64_t mtts_text_debug_buffer_offset(const MttsTextHandle* h, int B, int T_x, const char* name);
 
+/* ---- the step after the path: HiFi-GAN generator -----------------------------------------
+ * Replaces the body of Generator.forward(mel) -> wav                               reference hifigan/models.py:181-195
+ * (conv_pre, four ConvTranspose1d upsampling stages each followed by three ResBlock1 :14-98 whose outputs are averaged,
+ * conv_post, tanh; configuration hifigan/config.py v1 -- what main.py:134-150 loads).
+ * Same conventions as above: caller-owned buffers, no allocation, no synchronisation, errors as codes.
+ *   mel (B, num_mels, T) fp32          wav (B, 1, hop * T) fp32 in (-1, 1), hop = product of the upsampling rates (256)
+ * Every utterance is vocoded over all T frames (the reference passes the padded mel, main.py:197).
+ * Supported: 1..4 upsampling stages with even rate u and kernel size 2u (padding u / 2), upsample_initial_channel a
+ * multiple of 256 with upsample_initial_channel / 2^n_ups == 32; 1..3 resblocks per stage with odd kernel sizes and 1..3
+ * dilations each, (kernel - 1) * dilation <= 50; num_mels a multiple of 8, <= 128.
+ * The weight table lists the reference's state-dict keys AFTER remove_weight_norm() (models.py:197-205): "conv_pre.weight",
+ * "ups.0.weight" ... "resblocks.11.convs2.2.bias", "conv_post.bias".  A weight-normed checkpoint (`*.weight_g`, `*.weight_v`,
+ * what main.py:146-147 loads) is folded by the host first: weight = g * v / |v| with the norm over all but the first axis. */
+typedef struct MttsVocHandle MttsVocHandle;
+typedef struct MttsVocConfig {
+  int num_mels;                         /* 80 */
+  int upsample_initial_channel;         /* 512 */
+  int n_ups;                            /* 4 */
+  int upsample_rates[4];                /* 8 8 2 2 */
+  int upsample_kernel_sizes[4];         /* 16 16 4 4 */
+  int n_resblocks;                      /* 3 */
+  int resblock_kernel_sizes[3];         /* 3 7 11 */
+  int n_dilations;                      /* 3 */
+  int resblock_dilation_sizes[3][3];    /* 1 3 5 for each resblock */
+} MttsVocConfig;
+
+int mtts_voc_create(const MttsVocConfig* cfg, int device, MttsVocHandle** out);
+void mtts_voc_destroy(MttsVocHandle* h);
+int mtts_voc_num_weights(const MttsVocHandle* h);
+const char* mtts_voc_weight_name(const MttsVocHandle* h, int idx);
+int64_t mtts_voc_weight_numel(const MttsVocHandle* h, int idx);
+size_t mtts_voc_weight_arena_bytes(const MttsVocHandle* h);
+int mtts_voc_set_weight_arena(MttsVocHandle* h, void* dev_arena, size_t bytes, void* stream);   /* 1024-byte aligned */
+int mtts_voc_load_weight(MttsVocHandle* h, int idx, const float* dev_src, int64_t numel, void* stream);
+int mtts_voc_weights_loaded(const MttsVocHandle* h);
+int mtts_voc_hop_length(const MttsVocHandle* h);
+size_t mtts_voc_workspace_bytes(const MttsVocHandle* h, int B, int T);
+int mtts_voc_release_workspace(MttsVocHandle* h, const void* workspace, size_t workspace_bytes);
+/* use_graph != 0 captures the call's 79 launches into a CUDA graph (cached per pointers / shape; the stream must be
+ * capturable, i.e. not the legacy default stream) */
+int mtts_voc_generator_forward(MttsVocHandle* h, const float* mel, float* wav, void* workspace, size_t workspace_bytes, int B, int T,
+                               int use_graph, void* stream);
+int mtts_voc_last_launch_count(const MttsVocHandle* h);
+/* introspection used by the parity tests and the bench: stop after n kernel launches (n < 0: run everything); byte offset
+ * of a named intermediate ("mel16", "a_in", "x", "xa", "t_act", "r_raw", "r_act", "xs": channels-last fp16 [B][frames][C]
+ * of the current level) inside the workspace for (B, T), -1 for an unknown name; per-launch timing like
+ * mtts_debug_profile_begin / _end */
+int mtts_voc_debug_set_launch_limit(MttsVocHandle* h, int n);
+int64_t mtts_voc_debug_buffer_offset(const MttsVocHandle* h, int B, int T, const char* name);
+int mtts_voc_debug_profile_begin(MttsVocHandle* h, void* stream);
+int mtts_voc_debug_profile_end(MttsVocHandle* h, int max_entries, float* ms, int* kind, double* flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,12 @@ class MttsTextConfig(C.Structure):
                                        "prenet", "filter_channels_dp", "kernel_size_dp", "n_spks", "spk_emb_dim")]
 
 
+class MttsVocConfig(C.Structure):
+    _fields_ = [("num_mels", C.c_int), ("upsample_initial_channel", C.c_int), ("n_ups", C.c_int), ("upsample_rates", C.c_int * 4),
+                ("upsample_kernel_sizes", C.c_int * 4), ("n_resblocks", C.c_int), ("resblock_kernel_sizes", C.c_int * 3),
+                ("n_dilations", C.c_int), ("resblock_dilation_sizes", (C.c_int * 3) * 3)]
+
+
 class MttsError(RuntimeError):
     pass
 
@@ -77,6 +83,25 @@ SIGNATURES = {
     "mtts_text_last_launch_count": (C.c_int, [C.c_void_p]),
     "mtts_text_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "mtts_text_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "mtts_voc_create": (C.c_int, [C.POINTER(MttsVocConfig), C.c_int, C.POINTER(C.c_void_p)]),
+    "mtts_voc_destroy": (None, [C.c_void_p]),
+    "mtts_voc_num_weights": (C.c_int, [C.c_void_p]),
+    "mtts_voc_weight_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "mtts_voc_weight_numel": (C.c_int64, [C.c_void_p, C.c_int]),
+    "mtts_voc_weight_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "mtts_voc_set_weight_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mtts_voc_load_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mtts_voc_weights_loaded": (C.c_int, [C.c_void_p]),
+    "mtts_voc_hop_length": (C.c_int, [C.c_void_p]),
+    "mtts_voc_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "mtts_voc_release_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mtts_voc_generator_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p]),
+    "mtts_voc_last_launch_count": (C.c_int, [C.c_void_p]),
+    "mtts_voc_debug_set_launch_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "mtts_voc_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "mtts_voc_debug_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mtts_voc_debug_profile_end": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "mtts_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
 }

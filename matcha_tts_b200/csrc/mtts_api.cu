@@ -1383,3 +1383,4 @@ int mtts_debug_gemm(MttsHandle* h, const void* A, const void* W, const float* bi
 }  // extern "C"
 
 #include "mtts_text.inc"
+#include "mtts_voc.inc"
