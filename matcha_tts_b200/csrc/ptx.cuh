@@ -181,6 +181,20 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* des
       : "memory");
 }
 
+// TMA store of a shared-memory box (bulk async group): rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have READ their shared-memory source (it may be overwritten)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ... have completed (their global writes are performed)
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------ TMEM alloc
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {

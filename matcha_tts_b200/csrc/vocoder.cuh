@@ -20,9 +20,9 @@
 // CK = 64 channels per K chunk with the 128-byte swizzle; CK = 32 with the 64-byte swizzle for the 32-channel level.
 // BN = N tile = accumulator columns: 256 / 128 / 64 / 32 (the level's channel count, or 256 for the wide ups / conv_pre).
 //
-// Warp roles (352 threads, persistent over (utterance, row tile, N tile), one CTA per SM): warp 0 TMA producer of the
-// activation tiles, warp 1 TMEM allocator + MMA issuer, warp 2 TMA producer of the weight boxes (constants: no dependency
-// wait), warps 3-10 epilogue (4 warps for BN = 32) with two accumulator stages in TMEM.
+// Warp roles (persistent over (utterance, row tile, N tile)): warp 0 TMA producer of the activation tiles, warp 1 TMEM
+// allocator + MMA issuer, warp 2 TMA producer of the weight boxes (constants: no dependency wait), then the epilogue warps
+// (8 for BN = 256, one CTA per SM; 4 for the narrower tiles, 2-3 CTAs per SM) with two accumulator stages in TMEM.
 //
 // Fused epilogue (models.py:84-91, :183-193):  v = (acc + bias [+ res] [+ acc_in]) * scale;  out_raw = v;
 // out_act = leaky_relu(v, slope) -- the activation every consumer conv applies to its input is applied once, by the
@@ -42,6 +42,7 @@ struct VocConvParams {
   int n_chunks;          // Cin / CK
   int taps, dil;         // tap t reads row t0 + r + (t - taps / 2) * dil
   int wb;                // k-tiles per weight box
+  int w_resident;        // 1: one N tile and the whole filter fits the weight ring: loaded once per CTA, never released
   const float* bias;     // [N]
   const __half* res;     // [B * L][ld] or null
   const __half* acc_in;  // [B * L][ld] or null
@@ -52,26 +53,38 @@ struct VocConvParams {
   int w_hint, pdl_late;
 };
 
-constexpr int VOC_THREADS = 352;
 constexpr int VOC_MAX_HALO_ROWS = 178;   // 128 + (11 - 1) * 5
 constexpr int VOC_PAR_N = 2048;
 
+// Per-variant resources.  The 256-wide tiles own an SM (two 256-column accumulators = all of TMEM, 4 x 32 KB weight ring).
+// The narrower tiles are latency-bound per CTA -- an M128 x N32..128 x K16 MMA is 16-66 cycles of tensor work but a tap of
+// the issue loop, the TMA issue and the epilogue of a tile each cost hundreds -- so they run 2 (N = 128, 64) or 3 (N = 32)
+// CTAs per SM with 4 epilogue warps each, shallower rings, and (when the whole filter fits the ring: N = 32, and k = 3 at
+// N = 64) the weights loaded ONCE per CTA instead of once per tile.
 template <int CK, int BN>
 struct VocSmem {
+  static constexpr int CTAS = BN == 256 ? 1 : (BN == 32 ? 3 : 2);          // CTAs per SM
+  static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
+  static constexpr int THREADS = 96 + 32 * EPI_WARPS;
   static constexpr int A_STAGE = (VOC_MAX_HALO_ROWS * CK * 2 + 1023) / 1024 * 1024;
-  static constexpr int NA = 3;
+  static constexpr int NA = BN == 256 ? 3 : 2;
+  // narrow tiles: the epilogue moves its tiles by TMA (residual / running-sum loads and both stores as 32 x 32 boxes through
+  // three 2 KB buffers per warp, 64-byte swizzle) instead of register transposes -- it is the critical path there
+  static constexpr bool TMA_EPI = BN <= 64;
   static constexpr int W_TILE = BN * CK * 2;
-  static constexpr int WB_MAX = (32768 / W_TILE) < 16 ? (32768 / W_TILE) : 16;
+  static constexpr int WB_MAX = BN == 32 ? 4 : 1;   // k-tiles per weight box
   static constexpr int W_STAGE = WB_MAX * W_TILE;
-  static constexpr int NW = 4;
-  static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+  static constexpr int NW = BN == 128 ? 3 : (BN == 32 ? 3 : 4);
+  static constexpr int PAR_N = BN == 256 ? VOC_PAR_N : BN;
   static constexpr int OFF_W = NA * A_STAGE;
   static constexpr int OFF_STAGE = OFF_W + NW * W_STAGE;
-  static constexpr int OFF_PAR = OFF_STAGE + 8 * GEMM_STAGING_BYTES;
-  static constexpr int OFF_BAR = OFF_PAR + VOC_PAR_N * 4;
+  static constexpr int EPI_STAGING = TMA_EPI ? 3 * 2048 : GEMM_STAGING_BYTES;   // per epilogue warp
+  static constexpr int OFF_PAR = OFF_STAGE + EPI_WARPS * EPI_STAGING;
+  static constexpr int OFF_BAR = OFF_PAR + PAR_N * 4;
   static constexpr int TOTAL = OFF_BAR + 256;
+  static_assert(OFF_STAGE % 1024 == 0, "epilogue boxes sit on swizzle-atom boundaries");
   static_assert(W_TILE % 1024 == 0 && WB_MAX >= 1, "weight k-tiles are whole swizzle atoms");
-  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
+  static_assert(CTAS * (TOTAL + 1024) <= 233472, "CTAS of these must fit the 228 KB of shared memory of one SM");
 };
 
 // K-major operand tile stored as rows of 64 bytes (32 x 16-bit) with the 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B):
@@ -86,8 +99,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
 }
 
 template <int CK, int BN>
-__global__ void __launch_bounds__(VOC_THREADS, 1)
-voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const VocConvParams p) {
+__global__ void __launch_bounds__((VocSmem<CK, BN>::THREADS), (VocSmem<CK, BN>::CTAS))
+voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmRes,
+                const __grid_constant__ CUtensorMap tmAcc, const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmAct,
+                const VocConvParams p) {
   using SM = VocSmem<CK, BN>;
   static_assert(CK == 64 || CK == 32, "K chunk = one swizzle row");
   constexpr int NA = SM::NA, NW = SM::NW, EW = SM::EPI_WARPS;
@@ -103,7 +118,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = bars + 2 * NA + 2 * NW;   // [2]
   uint64_t* tempty = tfull + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  static_assert((2 * NA + 2 * NW + 5) * 8 <= 256, "barrier block");
+  uint64_t* ebar = tempty + 3;                // [2 * EW] (TMA epilogue): residual / running-sum box landed, per warp
+  static_assert((2 * NA + 2 * NW + 5 + (SM::TMA_EPI ? 2 * EW : 0)) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!p.pdl_late) pdl_launch_dependents();
@@ -118,14 +134,15 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EW); }
+    if (SM::TMA_EPI) for (int i = 0; i < 2 * EW; ++i) mbar_init(&ebar[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   if (warp >= 3) {
-    const int ncols = min(p.n_tiles * BN, VOC_PAR_N);
-    for (int i = threadIdx.x - 96; i < ncols; i += VOC_THREADS - 96) s_par[i] = p.bias ? p.bias[i] : 0.f;
+    const int ncols = min(p.n_tiles * BN, SM::PAR_N);
+    for (int i = threadIdx.x - 96; i < ncols; i += SM::THREADS - 96) s_par[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -139,6 +156,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint64_t pol = l2_policy_evict_last();
     const int ngroups = (KT + p.wb - 1) / p.wb;
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
+      if (p.w_resident && ti > 0) break;   // the filter stays where the first tile put it
       const int n0 = (tile % p.n_tiles) * BN;
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&wempty[stage], phase ^ 1);
@@ -171,21 +189,28 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
+    // The whole warp runs the loop converged (waits, address arithmetic); the tcgen05 instructions sit under elect.sync, which
+    // the compiler turns into uniform-datapath issue (a plain `lane == 0` test makes it loop over the "active" lanes instead).
+    // A tap of a narrow tile is 2-4 short MMAs: the loop around them has to cost less than they do.
     constexpr uint32_t idesc = umma_idesc_f16(128, BN);
     int sa = 0, sw = 0, as = 0;
     uint32_t pa = 0, pw = 0, aphase = 0;
     const uint32_t a_base = smem_u32(smem), w_base = smem_u32(smem + SM::OFF_W);
+    const uint32_t tap_step = (uint32_t)p.dil * (CK * 2);
+    const bool resident = p.w_resident != 0;
     for (int ti = 0; cta_tile(ti) >= 0; ++ti) {
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
+      const bool w_wait = !(resident && ti > 0);   // a resident filter is complete after the first tile
       int kt = 0, kw = 0;   // k-tile of the conv, k-tile inside the current weight box
+      if (resident) sw = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&afull[sa], pa);
-        for (int t = 0; t < p.taps; ++t, ++kt) {
-          if (kw == 0) mbar_wait(&wfull[sw], pw);
-          tc_fence_after();
-          const uint32_t a_addr = a_base + sa * SM::A_STAGE + t * p.dil * (CK * 2);
+        tc_fence_after();
+        uint32_t a_addr = a_base + sa * SM::A_STAGE;
+        for (int t = 0; t < p.taps; ++t, ++kt, a_addr += tap_step) {
+          if (kw == 0 && w_wait) { mbar_wait(&wfull[sw], pw); tc_fence_after(); }
           const uint32_t w_addr = w_base + sw * SM::W_STAGE + kw * SM::W_TILE;
           const uint64_t da = (CK == 64) ? umma_desc_sw128(a_addr) : umma_desc_sw64(a_addr);
           const uint64_t db = (CK == 64) ? umma_desc_sw128(w_addr) : umma_desc_sw64(w_addr);
@@ -193,16 +218,16 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < CK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kt | k) != 0);
-            if (last_of_box) umma_commit(&wempty[sw]);
-            if (t + 1 == p.taps) umma_commit(&aempty[sa]);
-            if (kt + 1 == KT) umma_commit(&tfull[as]);
+            if (last_of_box && !resident) umma_commit(&wempty[sw]);
           }
-          __syncwarp();
           if (last_of_box) { kw = 0; if (++sw == NW) { sw = 0; pw ^= 1; } }
           else ++kw;
         }
+        if (elect_one()) umma_commit(&aempty[sa]);
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -215,11 +240,115 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 3;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int cbase = (ew >> 2) * CW;
-    const uint32_t st = smem_u32(smem + SM::OFF_STAGE + ew * GEMM_STAGING_BYTES);
     const uint32_t spar = smem_u32(s_par);
     int as = 0;
     uint32_t aphase = 0;
     pdl_wait();   // residual reads, and stores into buffers the previous kernel may still be reading
+    if constexpr (SM::TMA_EPI) {
+      // Per warp three 32-row x 64-byte boxes in the 64-byte swizzle (16-byte unit u of row r at r * 64 + ((u ^ ((r >> 1) & 3)) << 4):
+      // what TMA reads / writes, and conflict-free for "thread = row" accesses): [0] residual, [1] running sum or raw output,
+      // [2] activated (or the only) output.  The residual / running-sum boxes of the NEXT chunk are requested as soon as this
+      // chunk has read them; the stores of a chunk overlap the next chunk's TMEM load and arithmetic.
+      const uint32_t sb = smem_u32(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING);
+      const uint32_t b_res = sb, b_one = sb + 2048, b_two = sb + 4096;
+      const uint32_t b_raw = p.out_act ? b_one : b_two;
+      uint64_t* rbar = &ebar[2 * ew];
+      uint64_t* abar = &ebar[2 * ew + 1];
+      const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
+      uint32_t lph = 0;
+      // coordinates of flattened chunk e = ti * NCH + ch of this warp: column, row inside the utterance, utterance; false past the end
+      auto chunk_at = [&](int e, int& col, int& row, int& bb) -> bool {
+        const int tile = cta_tile(e / NCH);
+        if (tile < 0) return false;
+        const int m = tile / p.n_tiles;
+        bb = m / p.tiles_per_utt;
+        row = (m % p.tiles_per_utt) * 128 + q * 32;
+        col = (tile % p.n_tiles) * BN + cbase + (e % NCH) * 32;
+        return true;
+      };
+      auto request = [&](int e) {   // lane 0
+        int col, row, bb;
+        if (!chunk_at(e, col, row, bb)) return;
+        if (has_res) { mbar_arrive_expect_tx(rbar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING), &tmRes, rbar, col, row, bb); }
+        if (has_acc) { mbar_arrive_expect_tx(abar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING + 2048), &tmAcc, abar, col, row, bb); }
+      };
+      auto add_box = [&](uint32_t box, float* v) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = lds128(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+          float2 f;
+          f = unpack_h2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+          f = unpack_h2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+          f = unpack_h2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+          f = unpack_h2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+        }
+      };
+      auto put_box = [&](uint32_t box, const float* v) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                 make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+                            pack_h2(v[8 * j + 6], v[8 * j + 7])));
+      };
+      if ((has_res || has_acc) && lane == 0) request(0);
+      int e = 0;
+      for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
+        const bool last_tile = p.pdl_late && cta_tile(ti + 1) < 0;
+        if (lane == 0) mbar_wait(&tfull[as], aphase);
+        __syncwarp();
+        tc_fence_after();
+        if (last_tile && lane == 0) pdl_launch_dependents();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + cbase;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch, ++e) {
+          int col, row, bb;
+          chunk_at(e, col, row, bb);
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch + 1 == NCH) {   // the accumulator is in registers: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = lds_f4(spar + (col + 4 * j) * 4);
+            v[4 * j + 0] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+          }
+          if (has_res) { mbar_wait(rbar, lph); add_box(b_res, v); }
+          if (has_acc) { mbar_wait(abar, lph); add_box(b_one, v); }
+          if (has_res || has_acc) {
+            lph ^= 1;
+            __syncwarp();                       // every lane has read its rows: the boxes may be refilled
+            if (lane == 0) request(e + 1);
+          }
+          if (p.scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+          }
+          if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's stores have read their boxes
+          __syncwarp();
+          if (p.out_raw) put_box(b_raw, v);
+          if (p.out_act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], p.slope * v[j]);   // 0 <= slope < 1
+            put_box(b_two, v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row < p.L) {
+            if (p.out_raw) tma_store_3d(&tmRaw, b_raw, col, row, bb);
+            if (p.out_act) tma_store_3d(&tmAct, b_two, col, row, bb);
+            tma_store_commit();
+          }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      if (lane == 0) tma_store_wait<0>();
+    } else {
+    const uint32_t st = smem_u32(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING);
     for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
       const int m = tile / p.n_tiles, b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * 128;
       const int n0 = (tile % p.n_tiles) * BN + cbase;
@@ -267,12 +396,13 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (p.out_raw) epi_store_h32(st, lane, v, p.out_raw + g0 + ch * 32, p.ld, rows_valid);
         if (p.out_act) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + p.slope * fminf(v[j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], p.slope * v[j]);   // 0 <= slope < 1
           epi_store_h32(st, lane, v, p.out_act + g0 + ch * 32, p.ld, rows_valid);
         }
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
+    }
     }
     if (p.pdl_late && cta_tile(0) < 0 && lane == 0) pdl_launch_dependents();
   }
