@@ -110,6 +110,35 @@ def load_reference():
     return mod
 
 
+def load_reference_hifigan():
+    """The reference's vendored HiFi-GAN Generator with config v1 (hifigan/models.py:148, config.py) or None.  xutils.py imports
+    matplotlib for a plotting helper the path never calls; when the image lacks it an empty stand-in module is registered."""
+    root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(root, "hifigan", "models.py")):
+        return None
+    import types
+    sys.dont_write_bytecode = True
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        m = types.ModuleType("matplotlib")
+        m.use = lambda *a, **k: None
+        m.pylab = types.ModuleType("matplotlib.pylab")
+        sys.modules["matplotlib"], sys.modules["matplotlib.pylab"] = m, m.pylab
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from hifigan.config import v1
+        from hifigan.env import AttrDict
+        from hifigan.models import Generator
+        import torch
+        torch.manual_seed(0)
+        gen = Generator(AttrDict(v1)).eval()
+    return gen
+
+
 def reference_cfm(ref, device="cpu"):
     """The reference's CFM around its Decoder with the hyper-parameters of reference main.py:67-75, seed 0, eval()."""
     import torch
@@ -323,6 +352,130 @@ def run_synthesize(dev, B, n_timesteps, steps, world):
             "h2d_bytes_per_call": tok_h.numel() * 8 + len_h.numel() * 8, "d2h_bytes_per_call": out_h.numel() * 4,
             "api": "MatchaTTS.synthesise(x, x_lengths, n_timesteps, temperature): native text encoder + duration predictor, alignment glue in "
                    "torch (one host read of y_lengths.max()), native CFM decoder; pinned-host tokens in, mels out, one call at a time"}
+
+
+def run_vocoder(dev, B, T, steps, cpu_budget_s=12.0):
+    """The step after the path: hifigan.Generator.forward(mel) -> wav on the native kernels, B x T
+    mel frames per call (the batch one solve produces).  `value`: mel resident in HBM, CUDA events on the launching stream;
+    `e2e`: pinned-host mel in, pinned-host waveform out inside the timed region; per-launch times for the roofline; the
+    reference's own Generator on the host cores (bounded sample) and through PyTorch eager on this GPU next to it."""
+    import ctypes as C
+    import torch
+    from matcha_tts_b200 import hifigan
+    from oracle import hifigan_oracle as HO          # weights only (seeded state-dict); the checker, not the thing measured
+    cfg = HO.HifiganCfg()
+    sd = HO.make_state_dict(cfg, 0)
+    gen = hifigan.Generator(hifigan.AttrDict(hifigan.v1))
+    gen.load_state_dict(HO.to_weight_norm(sd), strict=True)
+    gen = gen.to(dev)
+    g = torch.Generator().manual_seed(3)
+    NSET = 3
+    mels_h = [(-5.0 + 2.0 * torch.randn(B, 80, T, generator=g)).pin_memory() for _ in range(NSET)]
+    mels_d = [m.to(dev) for m in mels_h]
+    stream = torch.cuda.Stream(dev)
+    flop = HO.flops_per_frame(cfg) * B * T
+    with torch.cuda.stream(stream):
+        for i in range(3):
+            wav = gen(mels_d[i % NSET])
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            wav = gen(mels_d[i % NSET])
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        wav_h = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            w = gen(mels_h[i % NSET].to(dev, non_blocking=True))
+            wav_h.copy_(w, non_blocking=True)
+            stream.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+        finite = bool(torch.isfinite(wav_h).all()) and float(wav_h.abs().max()) <= 1.0
+        # per-launch device times (event pairs; graph bypassed meanwhile)
+        eng = gen._engine(dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device()))
+        lib = eng.lib
+        gen.use_cuda_graph = False
+        gen(mels_d[0])
+        best = None
+        for _ in range(2):
+            lib.mtts_voc_debug_profile_begin(eng.h, stream.cuda_stream)
+            gen(mels_d[0])
+            n = 128
+            tms, kind, fl = (C.c_float * n)(), (C.c_int * n)(), (C.c_double * n)()
+            cnt = lib.mtts_voc_debug_profile_end(eng.h, n, tms, kind, fl)
+            rows = [(tms[i], kind[i], fl[i]) for i in range(cnt)]
+            if best is None or sum(r[0] for r in rows) < sum(r[0] for r in best):
+                best = rows
+        gen.use_cuda_graph = True
+    gemm_ms = sum(r[0] for r in best if r[1] == 0)
+    gemm_fl = sum(r[2] for r in best if r[1] == 0)
+    peak, _, peak_src = measured_peaks()
+    out = {"value": B * T / (ms * 1e-3), "unit": UNIT, "ms_per_call": ms, "calls": steps, "batch": B, "frames": T,
+           "samples_per_call": B * T * cfg.hop, "x_real_time_22050": B * T * cfg.hop / 22050.0 / (ms * 1e-3),
+           "model_tflops": flop / (ms * 1e-3) / 1e12, "flop_per_mel_frame": HO.flops_per_frame(cfg), "finite": finite,
+           "launches_per_call": len(best),
+           "e2e": {"value": B * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_call": e2e_ms, "h2d_bytes_per_call": B * 80 * T * 4,
+                   "d2h_bytes_per_call": B * T * cfg.hop * 4,
+                   "api": "hifigan.Generator.forward(mel): pinned-host mel in, pinned-host waveform out, one call at a time"},
+           "roofline": {"bound": "tensor", "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}): the launches run inside a long step",
+                        "what": f"the {sum(1 for r in best if r[1] == 0)} voc_conv_kernel launches of one call, CUDA-event pairs per launch "
+                                f"({gemm_ms:.2f} ms of {sum(r[0] for r in best):.2f} ms), dense FLOPs at the real channel widths "
+                                "(the zero weights of the ConvTranspose phases and the padded mel channels are not counted)"},
+           "api": "matcha_tts_b200.hifigan.Generator(AttrDict(v1)).forward(mel) == reference hifigan/models.py:181-195; fp16 operands "
+                  "and activations, fp32 accumulate; 13.9 M parameters, seeded weights"}
+    # the reference's own Generator: host cores on a bounded sample, PyTorch eager on this GPU at the full batch
+    try:
+        ref = load_reference_hifigan()
+        if ref is not None:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref.load_state_dict(HO.to_weight_norm(sd), strict=True)
+            with torch.no_grad():
+                rows = 1
+                x = mels_h[0][:rows].clone()
+                t0 = time.perf_counter()
+                ref(x)
+                one = time.perf_counter() - t0
+                reps = max(1, min(5, int(cpu_budget_s / max(one, 1e-3)) - 1))
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    y_cpu = ref(x)
+                cpu_s = (time.perf_counter() - t0) / reps
+                out["cpu_baseline"] = {"value": rows * T / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                                       "sample": f"reference hifigan.models.Generator (staged baseline/_ref/hifigan), {rows} of {B} rows x T={T}, "
+                                                 f"fp32 torch-CPU, mean of {reps} after 1 warm-up"}
+                d = wav_h[:rows].double() - y_cpu.double()
+                out["vs_reference_wav"] = {"max_abs": float(d.abs().max()), "rel_l2": float(d.norm() / y_cpu.double().norm())}
+                refg = ref.to(dev)
+                res = {}
+                for name, ctx in (("eager_fp32_tf32conv", None), ("autocast_bf16", torch.bfloat16)):
+                    def run():
+                        if ctx is None:
+                            return refg(mels_d[0])
+                        with torch.autocast("cuda", dtype=ctx):
+                            return refg(mels_d[0])
+                    run()
+                    torch.cuda.synchronize(dev)
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    for _ in range(3):
+                        run()
+                    a1.record()
+                    a1.synchronize()
+                    t = a0.elapsed_time(a1) / 3
+                    res[name] = {"value": B * T / (t * 1e-3), "unit": UNIT, "ms_per_call": t}
+                out["reference_on_gpu"] = res
+                del refg
+    except Exception as exc:
+        out["reference_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    del gen, mels_d
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -636,6 +789,14 @@ def run_native(args):
         except Exception as exc:
             synth = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the step after the path: the HiFi-GAN generator on the batch one solve produces (rank 0, one GPU) ----
+    voc = None
+    if not args.no_vocoder and world == 1 and rank == 0:
+        try:
+            voc = run_vocoder(dev, B, T, max(5, args.steps // 2))
+        except Exception as exc:
+            voc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     ref_gpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         ref_gpu = reference_on_gpu(B, T, n, dev)
@@ -660,7 +821,7 @@ def run_native(args):
                 "sustained": sustained,
                 "serial": {"value": serial_value, "ms_per_step": serial_ms / args.steps, "ms_min": min(ms), "ms_max": max(ms),
                            "note": "one solve at a time (latency of a batch-64 solve), L2 flushed between steps"}}),
-            "roofline": roof, "cpu_baseline": cpu, "config5": config5, "synthesize": synth, "reference_on_gpu": ref_gpu,
+            "roofline": roof, "cpu_baseline": cpu, "config5": config5, "synthesize": synth, "vocoder": voc, "reference_on_gpu": ref_gpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": mu_h.numel() * 4 + mask_h.numel() * 4,
                     "d2h_bytes_per_step": out_h[0].numel() * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "CFM.forward(mu, mask, n_timesteps, temperature) per step, pinned-host mu/mask in and mel out per step; "
@@ -687,6 +848,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=120, help="extra timed region of this many steps (0 = skip)")
     ap.add_argument("--no-synthesize", action="store_true", help="skip the tokens -> mel leg (MatchaTTS.synthesise)")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the mel -> waveform leg (hifigan.Generator)")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 job folded into the line")
     ap.add_argument("--config5-utts", type=int, default=4096)
     ap.add_argument("--config5-frames", type=int, default=64 * 344, help="padded-frame budget per bucket")

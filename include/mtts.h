@@ -244,6 +244,19 @@ int64_t mtts_voc_debug_buffer_offset(const MttsVocHandle* h, int B, int T, const
 int mtts_voc_debug_profile_begin(MttsVocHandle* h, void* stream);
 int mtts_voc_debug_profile_end(MttsVocHandle* h, int max_entries, float* ms, int* kind, double* flops);
 
+/* ---- Denoiser (reference hifigan/denoiser.py:12-68): torch.stft / torch.istft with n_fft = win_length = 1024, hop 256,
+ * periodic Hann window, centred reflect-padded frames -- the configuration the reference constructs (filter_length 1024,
+ * n_overlap 4) -- as hand-written fp32 FFT kernels.  Handle-free: they run on `device` and restore the caller's device.
+ *   audio (B, n) fp32, n > 512          F = mtts_stft_frames(n) = 1 + n / 256 frames
+ *   mtts_stft_magnitude:  mag (B, 513, F) = |stft(audio)|                                                    denoiser.py:29-39
+ *   mtts_denoiser_forward: out (B, 256 * (F - 1)) = istft((|X| - bias_spec * strength)+ * exp(i arg X))      denoiser.py:62-68
+ *                          bias_spec: 513 floats (denoiser.py:60); workspace: mtts_stft_workspace_bytes(B, n), 16-byte aligned */
+int mtts_stft_frames(int n);
+size_t mtts_stft_workspace_bytes(int B, int n);
+int mtts_stft_magnitude(int device, const float* audio, float* mag, int B, int n, void* stream);
+int mtts_denoiser_forward(int device, const float* audio, const float* bias_spec, float strength, float* out, void* workspace,
+                          size_t workspace_bytes, int B, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

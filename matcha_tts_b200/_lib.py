@@ -102,6 +102,11 @@ SIGNATURES = {
     "mtts_voc_debug_buffer_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "mtts_voc_debug_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtts_voc_debug_profile_end": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "mtts_stft_frames": (C.c_int, [C.c_int]),
+    "mtts_stft_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mtts_stft_magnitude": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mtts_denoiser_forward": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                        C.c_void_p]),
     "mtts_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
 }

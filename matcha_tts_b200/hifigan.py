@@ -279,6 +279,75 @@ class Generator(nn.Module):
         return next(reversed(self._engines.values())).launch_count()
 
 
+class ModeException(Exception):
+    """hifigan/denoiser.py:7-8."""
+
+
+class Denoiser(nn.Module):
+    """Removes the vocoder's bias from generated audio; constructor / forward as reference hifigan/denoiser.py:12-68.
+
+    `vocoder` is any module mapping a (1, 80, 88) mel to a (1, 1, n) waveform on a CUDA device (normally the native Generator).
+    The STFT / inverse STFT run on libmtts' own FFT kernels (mtts_stft_magnitude, mtts_denoiser_forward)."""
+
+    def __init__(self, vocoder, filter_length=1024, n_overlap=4, win_length=1024, mode="zeros"):
+        super().__init__()
+        if filter_length != 1024 or n_overlap != 4 or win_length != 1024:
+            raise NotImplementedError("the native Denoiser implements the reference's configuration only: filter_length=1024, n_overlap=4, "
+                                      "win_length=1024")
+        self.filter_length = filter_length
+        self.hop_length = int(filter_length / n_overlap)
+        self.win_length = win_length
+        prm = next(vocoder.parameters())
+        dtype, device = prm.dtype, prm.device
+        if device.type != "cuda":
+            raise RuntimeError("matcha_tts_b200.hifigan.Denoiser runs on CUDA (sm_100a) only: move the vocoder to the GPU first")
+        self.device = device
+        self._lib = _lib.load()
+        if mode == "zeros":
+            mel_input = torch.zeros((1, 80, 88), dtype=dtype, device=device)
+        elif mode == "normal":
+            mel_input = torch.randn((1, 80, 88), dtype=dtype, device=device)
+        else:
+            raise ModeException(f"Mode {mode} if not supported")
+        with torch.no_grad():
+            bias_audio = vocoder(mel_input).float().squeeze(0)                    # (1, n)
+            bias_spec = self.stft_magnitude(bias_audio)                           # (1, 513, F)
+        self.register_buffer("bias_spec", bias_spec[:, :, 0][:, :, None].contiguous())
+        self._ws = None
+
+    def stft_magnitude(self, audio: torch.Tensor) -> torch.Tensor:
+        """|torch.stft(audio, 1024, hop 256, win 1024, periodic Hann, centred)| : (B, n) -> (B, 513, 1 + n // 256)."""
+        audio = audio.detach().to(torch.float32).contiguous()
+        B, n = audio.shape
+        F = self._lib.mtts_stft_frames(n)
+        mag = torch.empty(B, 513, F, dtype=torch.float32, device=audio.device)
+        _lib.check(self._lib.mtts_stft_magnitude(audio.device.index or 0, audio.data_ptr(), mag.data_ptr(), B, n,
+                                                 torch.cuda.current_stream(audio.device).cuda_stream))
+        return mag
+
+    @torch.inference_mode()
+    def forward(self, audio, strength=0.0005):
+        """audio (B, n) -> denoised audio (B, 256 * (n // 256))."""
+        if audio.ndim != 2:
+            raise ValueError(f"audio must be (B, n); got {tuple(audio.shape)}")
+        if audio.device.type != "cuda":
+            raise RuntimeError("matcha_tts_b200.hifigan.Denoiser runs on CUDA (sm_100a) only; there is no CPU path")
+        a = audio.detach().to(torch.float32).contiguous()
+        B, n = a.shape
+        nbytes = self._lib.mtts_stft_workspace_bytes(B, n)
+        if nbytes == 0:
+            raise _lib.MttsError(f"unsupported shape B={B}, n={n}: the centred frames need more than 512 samples")
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != a.device:
+            with torch.inference_mode(False):
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        out = torch.empty(B, 256 * (self._lib.mtts_stft_frames(n) - 1), dtype=torch.float32, device=a.device)
+        bias = self.bias_spec.to(device=a.device, dtype=torch.float32).contiguous()
+        _lib.check(self._lib.mtts_denoiser_forward(a.device.index or 0, a.data_ptr(), bias.data_ptr(), float(strength), out.data_ptr(),
+                                                   self._ws.data_ptr(), self._ws.numel(), B, n,
+                                                   torch.cuda.current_stream(a.device).cuda_stream))
+        return out
+
+
 def load_vocoder(path: str, device) -> Generator:
     """main.py:134-150 without the download: Generator(AttrDict(v1)), `state["generator"]` loaded strictly, eval mode, weight norm
     removed."""

@@ -15,3 +15,12 @@ mkdir -p "$ROOT/baseline/_ref"
 cp -f "$SRC/model.py" "$ROOT/baseline/_ref/model.py"
 chmod u+w "$ROOT/baseline/_ref/model.py"
 echo "staged $SRC/model.py -> baseline/_ref/model.py"
+# the vocoder row: the vendored HiFi-GAN package the reference calls after the mel (main.py:134-150)
+if [ -d "$SRC/hifigan" ]; then
+  mkdir -p "$ROOT/baseline/_ref/hifigan"
+  for f in __init__.py models.py config.py env.py xutils.py denoiser.py; do
+    cp -f "$SRC/hifigan/$f" "$ROOT/baseline/_ref/hifigan/$f"
+    chmod u+w "$ROOT/baseline/_ref/hifigan/$f"
+  done
+  echo "staged $SRC/hifigan/{models,config,env,xutils,denoiser}.py -> baseline/_ref/hifigan/"
+fi
