@@ -236,7 +236,7 @@ int mtts_voc_generator_forward(MttsVocHandle* h, const float* mel, float* wav, v
                                int use_graph, void* stream);
 int mtts_voc_last_launch_count(const MttsVocHandle* h);
 /* introspection used by the parity tests and the bench: stop after n kernel launches (n < 0: run everything); byte offset
- * of a named intermediate ("mel16", "a_in", "x", "xa", "t_act", "r_raw", "r_act", "xs": channels-last fp16 [B][frames][C]
+ * of a named intermediate ("mel16", "a_in", "xa", "t_act", "r_act", "xs": channels-last fp16 [B][frames][C]
  * of the current level) inside the workspace for (B, T), -1 for an unknown name; per-launch timing like
  * mtts_debug_profile_begin / _end */
 int mtts_voc_debug_set_launch_limit(MttsVocHandle* h, int n);

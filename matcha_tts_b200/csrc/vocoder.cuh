@@ -45,6 +45,9 @@ struct VocConvParams {
   int w_resident;        // 1: one N tile and the whole filter fits the weight ring: loaded once per CTA, never released
   const float* bias;     // [N]
   const __half* res;     // [B * L][ld] or null
+  float res_unslope;     // 0: `res` holds the residual itself.  u > 1: it holds leaky_relu(x, 1 / u) and x = min(a, u * a) is recovered
+                         //    from it -- the activated copy is all the stream keeps (fp16(x / u) * u carries the same 2^-11 relative
+                         //    rounding a raw fp16 copy would), which saves one store and one buffer per conv pair
   const __half* acc_in;  // [B * L][ld] or null
   __half* out_raw;       // [B * L][ld] or null
   __half* out_act;       // [B * L][ld] or null
@@ -96,6 +99,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;
   return d;
+}
+
+// epi_resid_add with the residual optionally recovered from its activated copy: x = min(a, un * a) (VocConvParams::res_unslope)
+__device__ __forceinline__ void voc_resid_add(uint32_t st, int lane, const uint4 (&rr)[4], float* v, float un) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) sts128(epi_st_addr(st, it * 8 + (lane >> 2), lane & 3), rr[it]);
+  __syncwarp();
+  const float m = (un != 0.f) ? un : 1.f;   // min(a, 1 * a) = a
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = lds128(epi_st_addr(st, lane, j));
+    float2 f;
+    f = unpack_h2(u.x); v[8 * j + 0] += fminf(f.x, f.x * m); v[8 * j + 1] += fminf(f.y, f.y * m);
+    f = unpack_h2(u.y); v[8 * j + 2] += fminf(f.x, f.x * m); v[8 * j + 3] += fminf(f.y, f.y * m);
+    f = unpack_h2(u.z); v[8 * j + 4] += fminf(f.x, f.x * m); v[8 * j + 5] += fminf(f.y, f.y * m);
+    f = unpack_h2(u.w); v[8 * j + 6] += fminf(f.x, f.x * m); v[8 * j + 7] += fminf(f.y, f.y * m);
+  }
 }
 
 template <int CK, int BN>
@@ -272,15 +292,18 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (has_res) { mbar_arrive_expect_tx(rbar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING), &tmRes, rbar, col, row, bb); }
         if (has_acc) { mbar_arrive_expect_tx(abar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING + 2048), &tmAcc, abar, col, row, bb); }
       };
-      auto add_box = [&](uint32_t box, float* v) {
+      auto add_box = [&](uint32_t box, float* v, float un) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 u = lds128(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+          float r[8];
           float2 f;
-          f = unpack_h2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-          f = unpack_h2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-          f = unpack_h2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-          f = unpack_h2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+          f = unpack_h2(u.x); r[0] = f.x; r[1] = f.y;
+          f = unpack_h2(u.y); r[2] = f.x; r[3] = f.y;
+          f = unpack_h2(u.z); r[4] = f.x; r[5] = f.y;
+          f = unpack_h2(u.w); r[6] = f.x; r[7] = f.y;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * j + i] += fminf(r[i], r[i] * un);   // un = 1: the value itself
         }
       };
       auto put_box = [&](uint32_t box, const float* v) {
@@ -316,8 +339,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const float4 bv = lds_f4(spar + (col + 4 * j) * 4);
             v[4 * j + 0] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
-          if (has_res) { mbar_wait(rbar, lph); add_box(b_res, v); }
-          if (has_acc) { mbar_wait(abar, lph); add_box(b_one, v); }
+          if (has_res) { mbar_wait(rbar, lph); add_box(b_res, v, p.res_unslope != 0.f ? p.res_unslope : 1.f); }
+          if (has_acc) { mbar_wait(abar, lph); add_box(b_one, v, 1.f); }
           if (has_res || has_acc) {
             lph ^= 1;
             __syncwarp();                       // every lane has read its rows: the boxes may be refilled
@@ -380,7 +403,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
         }
         if (p.res) {
-          epi_resid_add(st, lane, rr, v);
+          voc_resid_add(st, lane, rr, v, p.res_unslope);
           __syncwarp();
           if (ch + 1 < NCH) epi_resid_issue(rr, lane, p.res + g0 + (ch + 1) * 32, p.ld, rows_valid);
         }

@@ -169,7 +169,7 @@ def test_denoiser_against_reference_golden(name):
         e1 = float((out - ref).abs().max())
         print(f"{name} strength {s}: max-abs {e2:.2e} with the reference bias, {e1:.2e} with the native bias")
         assert e2 <= DEN_ABS, (name, s, e2)
-        assert e1 <= DEN_ABS + 10 * s * WAV_REL, (name, s, e1)
+        assert e1 <= DEN_ABS + 4e-4 * s, (name, s, e1)      # measured 3.4e-6 at strength 0.05
 
 
 def test_denoiser_errors():

@@ -24,7 +24,6 @@ def stages(cfg: HO.HifiganCfg):
     nk, nd = len(cfg.resblock_kernel_sizes), len(cfg.resblock_dilation_sizes[0])
     for i in range(len(cfg.upsample_rates)):
         n += 1
-        out.append((n, f"ups.{i}", "x", f"ups.{i}", None))
         out.append((n, f"ups.{i} act", "xa", f"ups.{i}", 0.1))
         for j in range(nk):
             for m in range(nd):
@@ -32,7 +31,6 @@ def stages(cfg: HO.HifiganCfg):
                 last_pair = m + 1 == nd
                 key = f"resblocks.{i * nk + j}.pair{m}"
                 if not last_pair:
-                    out.append((n, key, "r_raw", key, None))
                     out.append((n, key + " act", "r_act", key, 0.1))
                 elif j + 1 < nk:
                     out.append((n, f"xs after resblock {i * nk + j}", "xs", f"xs.{i}.{j}", None))
