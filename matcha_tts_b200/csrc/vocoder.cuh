@@ -71,9 +71,10 @@ struct VocSmem {
   static constexpr int THREADS = 96 + 32 * EPI_WARPS;
   static constexpr int A_STAGE = (VOC_MAX_HALO_ROWS * CK * 2 + 1023) / 1024 * 1024;
   static constexpr int NA = BN == 256 ? 3 : 2;
-  // narrow tiles: the epilogue moves its tiles by TMA (residual / running-sum loads and both stores as 32 x 32 boxes through
-  // three 2 KB buffers per warp, 64-byte swizzle) instead of register transposes -- it is the critical path there
-  static constexpr bool TMA_EPI = BN <= 64;
+  // narrow tiles: the epilogue moves its tiles by TMA (the residual load, requested one chunk ahead, and the store, as 32 x 32
+  // boxes through two 2 KB buffers per warp in the 64-byte swizzle) instead of register transposes -- it is the critical
+  // path there.  (Every launch has ONE output since the residual stream is kept in its activated form only.)
+  static constexpr bool TMA_EPI = BN <= 128;
   static constexpr int W_TILE = BN * CK * 2;
   static constexpr int WB_MAX = BN == 32 ? 4 : 1;   // k-tiles per weight box
   static constexpr int W_STAGE = WB_MAX * W_TILE;
@@ -81,7 +82,8 @@ struct VocSmem {
   static constexpr int PAR_N = BN == 256 ? VOC_PAR_N : BN;
   static constexpr int OFF_W = NA * A_STAGE;
   static constexpr int OFF_STAGE = OFF_W + NW * W_STAGE;
-  static constexpr int EPI_STAGING = TMA_EPI ? 3 * 2048 : GEMM_STAGING_BYTES;   // per epilogue warp
+  static constexpr int EPI_BOXES = BN == 128 ? 2 : 3;   // a third box (the resblocks' running sum, also prefetched) where it fits
+  static constexpr int EPI_STAGING = TMA_EPI ? EPI_BOXES * 2048 : GEMM_STAGING_BYTES;   // per epilogue warp
   static constexpr int OFF_PAR = OFF_STAGE + EPI_WARPS * EPI_STAGING;
   static constexpr int OFF_BAR = OFF_PAR + PAR_N * 4;
   static constexpr int TOTAL = OFF_BAR + 256;
@@ -265,16 +267,20 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     pdl_wait();   // residual reads, and stores into buffers the previous kernel may still be reading
     if constexpr (SM::TMA_EPI) {
-      // Per warp three 32-row x 64-byte boxes in the 64-byte swizzle (16-byte unit u of row r at r * 64 + ((u ^ ((r >> 1) & 3)) << 4):
-      // what TMA reads / writes, and conflict-free for "thread = row" accesses): [0] residual, [1] running sum or raw output,
-      // [2] activated (or the only) output.  The residual / running-sum boxes of the NEXT chunk are requested as soon as this
-      // chunk has read them; the stores of a chunk overlap the next chunk's TMEM load and arithmetic.
+      // Per warp two 32-row x 64-byte boxes in the 64-byte swizzle (16-byte unit u of row r at r * 64 + ((u ^ ((r >> 1) & 3)) << 4):
+      // what TMA reads / writes, and conflict-free for "thread = row" accesses): [0] the residual tile, requested for the NEXT chunk
+      // as soon as this chunk has read it, [1] the output tile, whose store overlaps the next chunk's TMEM load and arithmetic.
+      // The running sum of the resblocks (two launches per level) goes through a third box, prefetched like the residual, where
+      // shared memory allows (N <= 64); at N = 128 it is read straight from global memory, one 64-byte row per lane.
+      constexpr bool ACC_BOX = SM::EPI_BOXES == 3;
       const uint32_t sb = smem_u32(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING);
-      const uint32_t b_res = sb, b_one = sb + 2048, b_two = sb + 4096;
-      const uint32_t b_raw = p.out_act ? b_one : b_two;
+      const uint32_t b_res = sb, b_out = sb + 2048, b_acc = sb + 4096;
       uint64_t* rbar = &ebar[2 * ew];
       uint64_t* abar = &ebar[2 * ew + 1];
       const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
+      const float un = p.res_unslope != 0.f ? p.res_unslope : 1.f;   // min(a, 1 * a) = a
+      __half* const outp = p.out_act ? p.out_act : p.out_raw;
+      const CUtensorMap* const tm_out = p.out_act ? &tmAct : &tmRaw;
       uint32_t lph = 0;
       // coordinates of flattened chunk e = ti * NCH + ch of this warp: column, row inside the utterance, utterance; false past the end
       auto chunk_at = [&](int e, int& col, int& row, int& bb) -> bool {
@@ -289,31 +295,16 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       auto request = [&](int e) {   // lane 0
         int col, row, bb;
         if (!chunk_at(e, col, row, bb)) return;
-        if (has_res) { mbar_arrive_expect_tx(rbar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING), &tmRes, rbar, col, row, bb); }
-        if (has_acc) { mbar_arrive_expect_tx(abar, 2048); tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING + 2048), &tmAcc, abar, col, row, bb); }
-      };
-      auto add_box = [&](uint32_t box, float* v, float un) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 u = lds128(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
-          float r[8];
-          float2 f;
-          f = unpack_h2(u.x); r[0] = f.x; r[1] = f.y;
-          f = unpack_h2(u.y); r[2] = f.x; r[3] = f.y;
-          f = unpack_h2(u.z); r[4] = f.x; r[5] = f.y;
-          f = unpack_h2(u.w); r[6] = f.x; r[7] = f.y;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[8 * j + i] += fminf(r[i], r[i] * un);   // un = 1: the value itself
+        if (has_res) {
+          mbar_arrive_expect_tx(rbar, 2048);
+          tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING), &tmRes, rbar, col, row, bb);
+        }
+        if (ACC_BOX && has_acc) {
+          mbar_arrive_expect_tx(abar, 2048);
+          tma_load_3d(reinterpret_cast<void*>(smem + SM::OFF_STAGE + ew * SM::EPI_STAGING + 4096), &tmAcc, abar, col, row, bb);
         }
       };
-      auto put_box = [&](uint32_t box, const float* v) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
-                 make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
-                            pack_h2(v[8 * j + 6], v[8 * j + 7])));
-      };
-      if ((has_res || has_acc) && lane == 0) request(0);
+      if ((has_res || (ACC_BOX && has_acc)) && lane == 0) request(0);
       int e = 0;
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         const bool last_tile = p.pdl_late && cta_tile(ti + 1) < 0;
@@ -326,6 +317,15 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ch = 0; ch < NCH; ++ch, ++e) {
           int col, row, bb;
           chunk_at(e, col, row, bb);
+          uint4 ar[ACC_BOX ? 1 : 4];
+          if constexpr (!ACC_BOX) {
+            if (has_acc) {
+              const bool ok = row + lane < p.L;
+              const __half* ap = p.acc_in + ((size_t)bb * p.L + (ok ? row + lane : 0)) * p.ld + col;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ar[j] = ok ? ldg128(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+            }
+          }
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
           tmem_ld_wait();
@@ -339,30 +339,66 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const float4 bv = lds_f4(spar + (col + 4 * j) * 4);
             v[4 * j + 0] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
-          if (has_res) { mbar_wait(rbar, lph); add_box(b_res, v, p.res_unslope != 0.f ? p.res_unslope : 1.f); }
-          if (has_acc) { mbar_wait(abar, lph); add_box(b_one, v, 1.f); }
-          if (has_res || has_acc) {
+          if (has_res) {
+            mbar_wait(rbar, lph);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = lds128(b_res + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              float2 f;
+              f = unpack_h2(u.x); v[8 * j + 0] += fminf(f.x, f.x * un); v[8 * j + 1] += fminf(f.y, f.y * un);
+              f = unpack_h2(u.y); v[8 * j + 2] += fminf(f.x, f.x * un); v[8 * j + 3] += fminf(f.y, f.y * un);
+              f = unpack_h2(u.z); v[8 * j + 4] += fminf(f.x, f.x * un); v[8 * j + 5] += fminf(f.y, f.y * un);
+              f = unpack_h2(u.w); v[8 * j + 6] += fminf(f.x, f.x * un); v[8 * j + 7] += fminf(f.y, f.y * un);
+            }
+          }
+          if (ACC_BOX && has_acc) {
+            mbar_wait(abar, lph);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = lds128(b_acc + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              float2 f;
+              f = unpack_h2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+              f = unpack_h2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = unpack_h2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = unpack_h2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+            }
+          }
+          if (has_res || (ACC_BOX && has_acc)) {
             lph ^= 1;
             __syncwarp();                       // every lane has read its rows: the boxes may be refilled
             if (lane == 0) request(e + 1);
+          }
+          if constexpr (!ACC_BOX) {
+            if (has_acc) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f;
+                f = unpack_h2(ar[j].x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+                f = unpack_h2(ar[j].y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+                f = unpack_h2(ar[j].z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+                f = unpack_h2(ar[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+              }
+            }
           }
           if (p.scale != 1.f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           }
-          if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's stores have read their boxes
-          __syncwarp();
-          if (p.out_raw) put_box(b_raw, v);
           if (p.out_act) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], p.slope * v[j]);   // 0 <= slope < 1
-            put_box(b_two, v);
           }
+          if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's store has read the box
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(b_out + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                   make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+                              pack_h2(v[8 * j + 6], v[8 * j + 7])));
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row < p.L) {
-            if (p.out_raw) tma_store_3d(&tmRaw, b_raw, col, row, bb);
-            if (p.out_act) tma_store_3d(&tmAct, b_two, col, row, bb);
+          if (lane == 0 && row < p.L && outp) {
+            tma_store_3d(tm_out, b_out, col, row, bb);
             tma_store_commit();
           }
         }
