@@ -346,7 +346,43 @@ def run_synthesize(dev, B, n_timesteps, steps, world):
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # the whole reference pipeline for ONE sentence ("end-to-end RTF (text -> mel -> HiFi-GAN -> denoiser)",
+    # MOS_audiou_generator.ipynb:235-258: mean 0.0173): tokens on the host -> synthesise -> vocoder -> denoiser -> audio on the host
+    rtf = None
+    if world == 1:
+        try:
+            from matcha_tts_b200 import hifigan
+            from oracle import hifigan_oracle as HO          # seeded vocoder weights only
+            voc = hifigan.Generator(hifigan.AttrDict(hifigan.v1))
+            voc.load_state_dict(HO.to_weight_norm(HO.make_state_dict(HO.HifiganCfg(), 0)), strict=True)
+            voc = voc.to(dev)
+            tok1 = torch.randint(0, 178, (1, 120), generator=g).pin_memory()
+            len1 = torch.full((1,), 120, dtype=torch.long).pin_memory()
+            with torch.cuda.stream(stream):
+                den = hifigan.Denoiser(voc, mode="zeros")
+
+                def sentence():
+                    mel, ylen, _ = m.synthesise(tok1.to(dev, non_blocking=True), len1.to(dev, non_blocking=True), n_timesteps=n_timesteps,
+                                                temperature=0.667)
+                    audio = den(voc(mel).clamp(-1, 1).squeeze(1), strength=0.00025)
+                    a_h = audio.to("cpu", non_blocking=True)
+                    stream.synchronize()
+                    return a_h.shape[-1] / 22050.0
+                for _ in range(3):
+                    secs = sentence()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    secs = sentence()
+                call = (time.perf_counter() - t0) / 10
+            rtf = {"value": call / secs, "ms_per_sentence": call * 1e3, "audio_seconds": secs, "x_real_time": secs / call,
+                   "what": "one sentence of 120 tokens, host tokens in -> MatchaTTS.synthesise (10 Euler steps) -> hifigan.Generator -> "
+                           "Denoiser -> audio on the host, mean of 10 calls; the reference's notebook reports RTF 0.0173 for this chain "
+                           "(BASELINE.md section 1, other hardware)"}
+            del voc, den
+        except Exception as exc:
+            rtf = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     return {"value": world * frames / dt, "unit": "valid mel-frames/s", "ms_per_call": dt / steps * 1e3, "calls": steps, "batch": B,
+            "sentence_rtf": rtf,
             "tokens_per_utterance": Tx, "mel_frames_per_call": frames // steps, "text_encoder_ms": enc_ms,
             "text_encoder_launches": m.encoder.last_launch_count(),
             "h2d_bytes_per_call": tok_h.numel() * 8 + len_h.numel() * 8, "d2h_bytes_per_call": out_h.numel() * 4,

@@ -207,18 +207,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   float* s_par = reinterpret_cast<float*>(staging + GEMM_EPI_WARPS * GEMM_STAGING_BYTES);
   uint8_t* s_red = reinterpret_cast<uint8_t*>(s_par) + SM::PAR_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + SM::RED_BYTES);
-  uint64_t* full_bar = bars;                    // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* full_bar = bars;                    // [STAGES | TAP_B_STAGES] <= 8
+  uint64_t* empty_bar = bars + 8;               // [STAGES | TAP_B_STAGES]
+  uint64_t* tfull_bar = bars + 16;              // [2]
+  uint64_t* tempty_bar = bars + 18;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   // tap-sharing mode (p.tap3): the ring region is re-cut into an activation ring of TAP_A_STAGES x 17 KB (130 rows x 128 B)
-  // and a weight ring of STAGES x 32 KB; full_bar / empty_bar guard the weight ring, afull / aempty the activation ring
-  constexpr bool TAP3_OK = (BN == 256 && KSUB == 1 && CG == 1 && (EPI == EPI_STATS || EPI == EPI_PLAIN));
-  constexpr int TAP_A_BYTES = 17 * 1024, TAP_A_STAGES = 3, TAP_B_OFF = 52 * 1024, TAP_B_BYTES = BN * GEMM_BK * 2;
-  static_assert(!TAP3_OK || (TAP_A_STAGES * TAP_A_BYTES <= TAP_B_OFF && TAP_B_OFF + STAGES * TAP_B_BYTES <= STAGES * SM::STAGE_BYTES),
+  // and a weight ring of TAP_B_STAGES x 32 KB (CTA pair: x 16 KB, this CTA's half of the weight tile); full_bar / empty_bar
+  // guard the weight ring, afull / aempty the activation ring.  A pair with tap sharing pulls 17 + 3 x 16 = 65 KB from L2
+  // per K chunk and row tile, against 113 KB for the single CTA and 96 KB for the pair with one activation tile per tap.
+  constexpr bool TAP3_OK = (BN == 256 && KSUB == 1 && (EPI == EPI_STATS || EPI == EPI_PLAIN));
+  constexpr int TAP_A_BYTES = 17 * 1024, TAP_A_STAGES = 3, TAP_B_OFF = 52 * 1024, TAP_B_BYTES = (BN / CG) * GEMM_BK * 2;
+  constexpr int TAP_B_STAGES = (CG == 2) ? 8 : STAGES;
+  static_assert(!TAP3_OK || (TAP_A_STAGES * TAP_A_BYTES <= TAP_B_OFF && TAP_B_OFF + TAP_B_STAGES * TAP_B_BYTES <= STAGES * SM::STAGE_BYTES),
                 "tap-sharing rings must fit the stage ring");
-  static_assert(2 * STAGES + 5 <= 24, "barrier block");
+  static_assert(STAGES <= 8 && TAP_B_STAGES <= 8, "barrier block");
   uint64_t* afull = bars + 24;                  // [TAP_A_STAGES]
   uint64_t* aempty = bars + 27;                 // [TAP_A_STAGES]
   const bool tap3 = TAP3_OK && p.tap3 != 0;
@@ -254,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // twice their bytes; the peer's TMA instructions complete_tx on it -- the transaction count may run negative inside
     // a phase), its accumulator-empty barrier collects the epilogue warps of both CTAs; empty / accumulator-full
     // barriers are signalled in both CTAs by multicast commits
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], tap3 ? 1 : 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < (tap3 ? TAP_B_STAGES : STAGES); ++i) { mbar_init(&full_bar[i], tap3 ? 1 : 2); mbar_init(&empty_bar[i], 1); }
     if (tap3) for (int i = 0; i < TAP_A_STAGES; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CG); }
     fence_mbar_init();
@@ -295,12 +298,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sb = smem + TAP_B_OFF + stage * TAP_B_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
-          if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
-          else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+          if constexpr (CG == 2) {   // this CTA's half of the weight tile; both halves are counted on the leader's barrier
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * TAP_B_BYTES);
+            if (p.w_hint) tma_load_2d_pair_hint(sb, &tmB, lbar, kc * GEMM_BK, n0 + (int)crank * (BN / 2), pol);
+            else tma_load_2d_pair(sb, &tmB, lbar, kc * GEMM_BK, n0 + (int)crank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], TAP_B_BYTES);
+            if (p.w_hint) tma_load_2d_hint(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0, pol);
+            else tma_load_2d(sb, &tmB, &full_bar[stage], kc * GEMM_BK, n0);
+          }
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == TAP_B_STAGES) { stage = 0; phase ^= 1; }
       };
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         const int n0 = (tile % p.n_tiles) * BN;
@@ -372,8 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int c = 0; c < sg.nchunks; ++c) {
               mbar_wait(&aempty[stage], phase ^ 1);
               if (elect_one()) {
-                mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
-                tma_load_2d(smem + stage * TAP_A_BYTES, tm, &afull[stage], sg.col0 + c * GEMM_BK, r0 - 1);
+                if constexpr (CG == 2) {   // both CTAs' tiles are counted on the leader's barrier
+                  if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * 130 * GEMM_BK * 2);
+                  tma_load_2d_pair(smem + stage * TAP_A_BYTES, tm, mapa_u32(smem_u32(&afull[stage]), 0), sg.col0 + c * GEMM_BK, r0 - 1);
+                } else {
+                  mbar_arrive_expect_tx(&afull[stage], 130 * GEMM_BK * 2);
+                  tma_load_2d(smem + stage * TAP_A_BYTES, tm, &afull[stage], sg.col0 + c * GEMM_BK, r0 - 1);
+                }
               }
               __syncwarp();
               if (++stage == TAP_A_STAGES) { stage = 0; phase ^= 1; }
@@ -438,14 +453,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint64_t da = umma_desc_sw128(smem_u32(smem + sa_i * TAP_A_BYTES) + t * (GEMM_BK * 2));
             const uint64_t db = umma_desc_sw128(smem_u32(smem + TAP_B_OFF + stage * TAP_B_BYTES));
             if (elect_one()) {
+              if constexpr (CG == 2) {
 #pragma unroll
-              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
-              umma_commit(&empty_bar[stage]);
-              if (t == 2) umma_commit(&aempty[sa_i]);
-              if (t == 2 && c + 1 == CH) umma_commit(&tfull_bar[has_res ? 0 : as]);
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                umma_commit_pair(&empty_bar[stage]);
+                if (t == 2) umma_commit_pair(&aempty[sa_i]);
+                if (t == 2 && c + 1 == CH) umma_commit_pair(&tfull_bar[has_res ? 0 : as]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                umma_commit(&empty_bar[stage]);
+                if (t == 2) umma_commit(&aempty[sa_i]);
+                if (t == 2 && c + 1 == CH) umma_commit(&tfull_bar[has_res ? 0 : as]);
+              }
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == TAP_B_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++sa_i == TAP_A_STAGES) { sa_i = 0; sa_ph ^= 1; }
         }
@@ -459,14 +482,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint64_t da = umma_desc_sw128(smem_u32(smem + sa_i * TAP_A_BYTES) + GEMM_BK * 2);   // shift 0 = one row in
             const uint64_t db = umma_desc_sw128(smem_u32(smem + TAP_B_OFF + stage * TAP_B_BYTES));
             if (elect_one()) {
+              if constexpr (CG == 2) {
 #pragma unroll
-              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem + BN, da + 2 * k, db + 2 * k, idesc, (c | k) != 0);
-              umma_commit(&empty_bar[stage]);
-              umma_commit(&aempty[sa_i]);
-              if (c + 1 == CH) umma_commit(&tfull_bar[1]);
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_pair(d_tmem + BN, da + 2 * k, db + 2 * k, idesc, (c | k) != 0);
+                umma_commit_pair(&empty_bar[stage]);
+                umma_commit_pair(&aempty[sa_i]);
+                if (c + 1 == CH) umma_commit_pair(&tfull_bar[1]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem + BN, da + 2 * k, db + 2 * k, idesc, (c | k) != 0);
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&aempty[sa_i]);
+                if (c + 1 == CH) umma_commit(&tfull_bar[1]);
+              }
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == TAP_B_STAGES) { stage = 0; phase ^= 1; }
             if (++sa_i == TAP_A_STAGES) { sa_i = 0; sa_ph ^= 1; }
           }
         }

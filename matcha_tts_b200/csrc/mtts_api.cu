@@ -229,6 +229,7 @@ struct MttsHandle {
                             // partition while the stand-alone pass has ~40 warps per SM -- profiles/r02_gnbqkv_*.txt
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
+  bool pair_tap3 = true;  // CTA pairs use tap sharing as well (MTTS_PAIR_TAP3=0: one activation tile per tap, the round-1 pair kernel)
   bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
                           // pair launches measured -1% (4.57 vs 4.63 M frames/s) although the kernel alone gains 5-10% at full occupancy
   bool pdl_late = true;  // GEMM / tail / attention CTAs release their dependents (griddepcontrol.launch_dependents) when their last
@@ -589,26 +590,10 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
     if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
       int chunks = 0;
       for (int i = 0; i < p.num_segs; ++i) chunks += p.seg[i].nchunks;
-      // tcgen05 cta_group::2: a CTA pair per 256-row tile, each CTA staging half of the weight tile.  Pays off for long K
-      // (tools/gemm_repeat.py at 692 row tiles: K=1536 1221 vs 1111 TFLOP/s, K=768 1090 vs 1035, K=256 518 vs 597)
-      if (h->cta_pairs && chunks >= h->pair_min_chunks) {
-        if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
-        const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
-        const int units = ((m_tiles + 1) / 2) * p.n_tiles;
-        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
-        GemmParams pp = p;
-        pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
-        pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
-        CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
-                               stream, a0.d2, a1.d2, wmap.d2h, pp));
-        launched(h);
-        return 0;
-      }
-    }
-    if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
       // k3 conv over one or two sources (+ res_conv): the three taps share one (128 + 2)-row activation tile per K chunk
+      int nsrc = 0;
       if (h->tap3) {
-        const int nsrc = (p.num_segs == 3 || p.num_segs == 4) ? 1 : ((p.num_segs == 6 || p.num_segs == 8) ? 2 : 0);
+        nsrc = (p.num_segs == 3 || p.num_segs == 4) ? 1 : ((p.num_segs == 6 || p.num_segs == 8) ? 2 : 0);
         const bool has_res = nsrc && p.num_segs == 4 * nsrc;
         bool ok = nsrc > 0;
         int CH = 0;
@@ -619,11 +604,30 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
             ok = g.src == s && g.row_shift == (t < 3 ? t - 1 : 0) && g.col0 == p.seg[s].col0 && g.nchunks == p.seg[s].nchunks;
           }
         ok = ok && p.res_chunk0 == (has_res ? 3 * CH : 0);
-        if (ok) {
-          GemmParams q = p;
-          q.tap3 = nsrc;
-          return launch_gemm_maps<256, EPI, 1>(h, a0.d2t, nsrc == 2 ? a1.d2t : a0.d2t, wmap.d2, q, stream, aflops);
-        }
+        if (!ok) nsrc = 0;
+      }
+      // tcgen05 cta_group::2: a CTA pair per 256-row tile, each CTA staging half of the weight tile.  Pays off for long K
+      // (tools/gemm_repeat.py at 692 row tiles: K=1536 1221 vs 1111 TFLOP/s, K=768 1090 vs 1035, K=256 518 vs 597); with
+      // tap sharing on top the pair pulls 65 KB per K chunk and row tile from L2 instead of 96 KB
+      if (h->cta_pairs && chunks >= h->pair_min_chunks) {
+        if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
+        const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+        const int units = ((m_tiles + 1) / 2) * p.n_tiles;
+        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+        GemmParams pp = p;
+        pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
+        pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
+        const bool t3 = nsrc > 0 && h->pair_tap3;
+        pp.tap3 = t3 ? nsrc : 0;
+        CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
+                               stream, t3 ? a0.d2t : a0.d2, t3 ? (nsrc == 2 ? a1.d2t : a0.d2t) : a1.d2, wmap.d2h, pp));
+        launched(h);
+        return 0;
+      }
+      if (nsrc > 0) {
+        GemmParams q = p;
+        q.tap3 = nsrc;
+        return launch_gemm_maps<256, EPI, 1>(h, a0.d2t, nsrc == 2 ? a1.d2t : a0.d2t, wmap.d2, q, stream, aflops);
       }
     }
     return launch_gemm_maps<BN, EPI, 1>(h, a0.d2, a1.d2, wmap.d2, p, stream, aflops);
@@ -988,6 +992,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   h->num_sms = 148;
   if (const char* e = getenv("MTTS_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = getenv("MTTS_PAIRS")) h->cta_pairs = (e[0] == '1');
+  if (const char* e = getenv("MTTS_PAIR_TAP3")) h->pair_tap3 = (e[0] == '1');
   if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');

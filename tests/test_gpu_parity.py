@@ -446,12 +446,16 @@ def test_chains_setting_keeps_results(lj):
 # ---------------------------------------------------------------------------------------------
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV", "MTTS_QKV_GEMM"])
+@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_PAIRS:one_tile_per_tap", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV",
+                                 "MTTS_QKV_GEMM"])
 def test_opt_in_variants(env):
+    env, _, sub = env.partition(":")
     old = os.environ.get(env)
     os.environ[env] = "1"
     if env == "MTTS_PAIRS":
         os.environ["MTTS_PAIR_MIN_CHUNKS"] = "0"
+        if sub:                      # the CTA-pair GEMM without tap sharing (one activation tile per tap)
+            os.environ["MTTS_PAIR_TAP3"] = "0"
     try:
         dec, cfg, sd = U.make_decoder(160)
         mu, mask, z0, _ = O.make_inputs(cfg, 3, 344, [344, 301, 222], seed=80)
@@ -466,6 +470,7 @@ def test_opt_in_variants(env):
                 _check_gemm(eng, rows, Cc, N, shifts)
     finally:
         os.environ.pop("MTTS_PAIR_MIN_CHUNKS", None)
+        os.environ.pop("MTTS_PAIR_TAP3", None)
         if old is None:
             os.environ.pop(env, None)
         else:
