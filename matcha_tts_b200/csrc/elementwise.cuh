@@ -220,6 +220,144 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same pass with the rows staged through shared memory by ONE bulk copy per block (default).
+// gn_apply_kernel above keeps its operands in registers while they are in flight: 4 rows x 512 B per warp at ~18 warps
+// per SM (110 registers) = 36 KB per SM, against the ~45 KB per SM that 6.5 TB/s x ~1 us of loaded HBM latency needs --
+// it ran at 3.6-4.3 TB/s (profiles/r02v_ncu_stage01_summary.txt).  Here a block of GN2_ROWS rows of one utterance issues
+// cp.async.bulk for its whole 32 KB slab of y (and of res, MODE 1) the moment the previous kernel has completed, finalises
+// the statistics and fetches its per-row operands while the bytes fly, and then streams the rows out of shared memory:
+// 32-64 KB in flight per block and several blocks per SM, no registers tied up.  The arithmetic is gn_apply_kernel's,
+// operation for operation (same bits; gnb_qkv_kernel relies on that too).
+// grid = (ceil(Lp / GN2_ROWS), B), block = 256 (8 warps x GN2_ROWS / 8 rows, 8 channels per lane).  Which of the two kernels a
+// launch gets is decided in mtts_api.cu::launch_gn (this one where throughput counts, the register-staged one for one small
+// solve at a time: its chain is shorter -- no barrier, no TMA round trip; 32-row blocks measured between the two)
+// ---------------------------------------------------------------------------------------------
+constexpr int GN2_THREADS = 256;
+template <int MODE, int GN2_ROWS>
+constexpr int gn2_smem_bytes() { return 128 + GN2_ROWS * 512 * (MODE == 1 ? 2 : 1); }
+
+template <int MODE, int GN2_ROWS>
+__global__ void __launch_bounds__(GN2_THREADS) gn_apply2_kernel(const GnParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gsm);
+  uint8_t* sy = gsm + 128;
+  uint8_t* sr = sy + GN2_ROWS * 512;
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = lane * 8, g = lane >> 2;
+  const int t0 = blockIdx.x * GN2_ROWS;
+  const int nload = min(GN2_ROWS, p.L - t0);   // rows of this block that exist in y (the rest, up to Lp, are guard rows)
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  // weights do not depend on the previous kernel: fetch them while it drains
+  float ga[8], be[8], te[8], lg[8], lb[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + c0), g1 = *reinterpret_cast<const float4*>(p.gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p.beta + c0), b1 = *reinterpret_cast<const float4*>(p.beta + c0 + 4);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+    if (MODE == 1) {
+      const float4 l0 = *reinterpret_cast<const float4*>(p.ln_g + c0), l1 = *reinterpret_cast<const float4*>(p.ln_g + c0 + 4);
+      const float4 m0 = *reinterpret_cast<const float4*>(p.ln_b + c0), m1 = *reinterpret_cast<const float4*>(p.ln_b + c0 + 4);
+      lg[0] = l0.x; lg[1] = l0.y; lg[2] = l0.z; lg[3] = l0.w; lg[4] = l1.x; lg[5] = l1.y; lg[6] = l1.z; lg[7] = l1.w;
+      lb[0] = m0.x; lb[1] = m0.y; lb[2] = m0.z; lb[3] = m0.w; lb[4] = m1.x; lb[5] = m1.y; lb[6] = m1.z; lb[7] = m1.w;
+    }
+  }
+  __syncthreads();   // the barrier is initialised before anyone polls it
+  pdl_wait();
+  if (threadIdx.x == 0 && nload > 0) {
+    const size_t row0 = (size_t)b * p.Lp + t0;
+    const uint32_t bytes = (uint32_t)nload * 512u;
+    mbar_arrive_expect_tx(bar, bytes * (MODE == 1 ? 2u : 1u));
+    bulk_load_1d(sy, p.y + row0 * 256, bytes, bar);
+    if (MODE == 1) bulk_load_1d(sr, p.res + row0 * 256, bytes, bar);
+  }
+  // per-row masks, time embedding and statistics partials travel while the slab does
+  constexpr int RPW = GN2_ROWS / 8;
+  const int tw0 = t0 + warp * RPW;
+  float m[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) m[i] = (tw0 + i < p.L) ? p.rowmask[(size_t)b * p.Lp + tw0 + i] : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) te[j] = 0.f;
+  if (MODE == 0 && p.temb) {
+    const float* tp = p.temb + (size_t)(p.t_off + b * p.t_stride) * p.t_ld + c0;
+    const float4 t0v = *reinterpret_cast<const float4*>(tp), t1v = *reinterpret_cast<const float4*>(tp + 4);
+    te[0] = t0v.x; te[1] = t0v.y; te[2] = t0v.z; te[3] = t0v.w; te[4] = t1v.x; te[5] = t1v.y; te[6] = t1v.z; te[7] = t1v.w;
+  }
+  float mean, rstd;
+  {
+    const int first = (b * p.Lp) >> 5, last = (b * p.Lp + p.L - 1) >> 5;
+    float s = 0.f, ss = 0.f;
+    for (int sl = lane & 3; sl <= last - first; sl += 4) {
+      const float2 pp = *reinterpret_cast<const float2*>(p.stats_part + ((size_t)b * p.S + sl) * 16 + 2 * g);
+      s += pp.x;
+      ss += pp.y;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float inv_n = 1.f / (32.f * (float)p.L);
+    mean = s * inv_n;
+    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ss * inv_n), 0.f) + 1e-5f);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] *= rstd;
+    be[j] = be[j] - mean * ga[j];
+  }
+  if (nload > 0) mbar_wait(bar, 0);
+  const uint32_t sya = smem_u32(sy) + c0 * 2, sra = smem_u32(sr) + c0 * 2;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int t = tw0 + i;
+    if (t >= p.Lp) break;   // warp-uniform
+    const size_t row = (size_t)b * p.Lp + t;
+    uint4 o = make_uint4(0, 0, 0, 0), o2 = make_uint4(0, 0, 0, 0);
+    if (t < p.L) {
+      const uint4 yv = lds128(sya + (t - t0) * 512);
+      float v[8];
+      float2 f;
+      f = unpack_h2(yv.x); v[0] = f.x; v[1] = f.y;
+      f = unpack_h2(yv.y); v[2] = f.x; v[3] = f.y;
+      f = unpack_h2(yv.z); v[4] = f.x; v[5] = f.y;
+      f = unpack_h2(yv.w); v[6] = f.x; v[7] = f.y;
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + te[j]) * m[i];
+      } else {
+        const uint4 rv = lds128(sra + (t - t0) * 512);
+        float r[8];
+        f = unpack_h2(rv.x); r[0] = f.x; r[1] = f.y;
+        f = unpack_h2(rv.y); r[2] = f.x; r[3] = f.y;
+        f = unpack_h2(rv.z); r[4] = f.x; r[5] = f.y;
+        f = unpack_h2(rv.w); r[6] = f.x; r[7] = f.y;
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = mish_f(fmaf(v[j], ga[j], be[j])) * m[i] + r[j];
+          s += v[j];
+          ss = fmaf(v[j], v[j], ss);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, off);
+          ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        }
+        const float lmean = s * (1.f / 256.f);
+        const float lrstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - lmean * lmean, 0.f) + 1e-5f);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf((v[j] - lmean) * lrstd, lg[j], lb[j]);
+        o2 = make_uint4(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]), pack_h2(a[4], a[5]), pack_h2(a[6], a[7]));
+      }
+      o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+    stg128(p.out + row * 256 + c0, o);  // guard rows are written as zeros
+    if (MODE == 1) stg128(p.out2 + row * 256 + c0, o2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // time path (data independent, reference model.py:753-762, :828-832, :780)
 // ---------------------------------------------------------------------------------------------
 // t values of the fixed-step solver: t_i = i/n in double, rounded to fp32 like the reference's

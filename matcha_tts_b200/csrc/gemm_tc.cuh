@@ -106,6 +106,11 @@ struct GemmParams {
                    //    all three taps through row-shifted shared-memory descriptors (tools/ubench/rowshift.cu); the res_conv pass
                    //    stages the tiles once more and reads them one row in
   int relu;        // EPI_PLAIN: 1 = ReLU after bias (+ residual), before the row mask (text encoder FFN / duration predictor convs)
+  int tma_out;     // 1 (256-wide STATS / PLAIN tiles): the fp16 output tiles leave as 32 x 32 TMA boxes (tmOut; the res_conv half through
+                   //    tmRes) straight from the per-warp staging tile, whose layout IS the 64-byte swizzle, instead of the
+                   //    shared-memory transpose + 64-byte-per-row st.global: per-tile stamps (tools/conv_tiles.py) showed the epilogue
+                   //    -- 2.6-3.2 us per 128 x 256 tile, 4.8 us with the res_conv half -- bounding the tile period once the operands
+                   //    arrive fast enough (CTA pairs), and the unit GEMM runs 20 % faster with its st.global removed
   int m_major;     // 1: a CTA owns whole row tiles and walks their N tiles back to back (launch grid <= row tiles):
                    //    the epilogue of one N tile overlaps the main loop of the next even with one row tile per CTA
 };
@@ -155,6 +160,26 @@ __device__ __forceinline__ void epi_store_h32(uint32_t st, int lane, const float
   }
   __syncwarp();
 }
+// the same tile handed to TMA: the staging layout is the 64-byte swizzle of a {32 columns, 32 rows} box; rows past the
+// tensor's end are clipped.  Lane 0 owns the bulk groups of its warp.
+__device__ __forceinline__ void epi_staging_acquire(int lane) {   // the previous TMA store has read the staging tile
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+}
+__device__ __forceinline__ void epi_store_h32_tma(uint32_t st, int lane, const float* v, const CUtensorMap* tm, int col, int row0,
+                                                  int rows_valid) {
+  epi_staging_acquire(lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128(epi_st_addr(st, lane, j), make_uint4(pack_h2(v[8 * j + 0], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7])));
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && rows_valid > 0) {
+    tma_store_2d(tm, st, col, row0);
+    tma_store_commit();
+  }
+}
 // issue the coalesced loads of a 32x32 fp16 residual tile (consumed later by epi_resid_add)
 __device__ __forceinline__ void epi_resid_issue(uint4 (&rr)[4], int lane, const __half* gtile, int ld, int rows_valid) {
 #pragma unroll
@@ -186,7 +211,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <int BN, int EPI, int KSUB = 1, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using SM = GemmSmem<BN, EPI, KSUB, CG>;
   static_assert(KSUB == 1 || (KSUB == 2 && BN == 128), "two K chunks per stage only for the 128-wide N tile");
   static_assert(CG == 1 || (CG == 2 && BN == 256 && KSUB == 1 && (EPI == EPI_STATS || EPI == EPI_PLAIN)), "CTA pairs: 256-wide conv tiles");
@@ -264,6 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmRes); }
   }
   if (warp == 1) {
     if constexpr (CG == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -581,6 +608,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE + cbase;
 
       if constexpr (EPI == EPI_STATS || EPI == EPI_PLAIN) {
+        const bool tma_out = (BN == 256) && p.tma_out != 0;
         const bool has_res = (EPI == EPI_PLAIN && p.resid != nullptr);
         const __half* rbase = has_res ? p.resid + (size_t)rw0 * p.ldr + n0 + cbase : nullptr;
         uint4 rr[4];
@@ -612,6 +640,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
           if (has_res) {
+            if (tma_out) epi_staging_acquire(lane);
             epi_resid_add(st, lane, rr, v);
             if (c + 1 < NCH) epi_resid_issue(rr, lane, rbase + (c + 1) * 32, p.ldr, rows_valid);
           }
@@ -629,7 +658,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (mrow == 0.f) ? 0.f : v[j] * mrow;  // never NaN * 0 on guard rows
           }
-          epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid, p.dbg);
+          if (tma_out) epi_store_h32_tma(st, lane, v, &tmOut, n0 + cbase + c * 32, rw0, rows_valid);
+          else epi_store_h32(st, lane, v, obase + c * 32, p.ldo, rows_valid, p.dbg);
           if (tl && ew == 0 && lane == 0 && ti == 0) tl[12 + (c != 0)] = clock64();
         }
         if constexpr (EPI == EPI_STATS) {
@@ -654,6 +684,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           } else {  // utterance boundary inside the warp's rows: serial, fixed order
+            if (tma_out) epi_staging_acquire(lane);
             const uint32_t sf = st;                 // [32][9] floats
             const uint32_t sb = st + 32 * 9 * 4;    // [32] ints
 #pragma unroll
@@ -703,7 +734,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const float4 b4 = lds_f4(spar + (256 + n0 + cbase + c * 32 + 4 * j) * 4);
                 v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
               }
-              epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
+              if (tma_out) epi_store_h32_tma(st, lane, v, &tmRes, n0 + cbase + c * 32, rw0, rows_valid);
+              else epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
             }
           }
         }
@@ -788,6 +820,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (dual_split) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
+    if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN))
+      if (p.tma_out && lane == 0) tma_store_wait<0>();   // the boxes are in global memory before the CTA retires
   }
 
   tc_fence_before();

@@ -95,6 +95,24 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return 0;
 }
 
+// fp16 2-D row-major output [rows, cols]: box = (32 cols, 32 rows) in the 64-byte swizzle = one epilogue warp's staging tile
+static int make_out_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(out) failed (%d) rows=%llu cols=%llu pitch=%llu", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch);
+    return fail(MTTS_ECUDA, buf);
+  }
+  return 0;
+}
+
 // fp16 [rows, nk*64] row-major viewed as [nk][rows][64]: one box = nk K-chunks of box_rows x 64, landing in
 // shared memory as nk consecutive 128B-swizzled tiles (a single TMA instruction for a whole operand piece)
 static int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint32_t nk, uint64_t pitch, uint32_t box_rows,
@@ -218,6 +236,10 @@ struct MttsHandle {
   int launch_count = 0, launch_limit = -1;
   bool a_prefetch = true;  // early L2 prefetch of the first activation tiles
   bool w_hint = true;      // weights are loaded with the L2 evict_last hint
+  bool tma_out = true;      // 256-wide conv / linear tiles leave the epilogue as 32 x 32 TMA boxes (MTTS_NO_TMA_OUT=1: shared-memory transpose +
+                            // st.global, same bits)
+  int gn_mode = 0;          // GroupNorm-apply pass: 0 = by launch size / concurrency (launch_gn), 1 = always the register-staged
+                            // gn_apply_kernel (MTTS_GN_REGS=1), 2 = always the bulk-staged gn_apply2_kernel (MTTS_GN_BULK=1); same bits
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
   bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
   bool qkv_gemm = false;    // MTTS_QKV_GEMM=1: the QKV projection through the generic gemm_tc_kernel<128, EPI_QKV> (one unit per N tile,
@@ -544,6 +566,19 @@ static cudaError_t launch_k_pair(const MttsHandle* h, void (*kern)(KArgs...), di
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// GroupNorm-apply pass (elementwise.cuh): rows staged by one bulk copy per block, or the register-staged form
+template <int MODE>
+static cudaError_t launch_gn(const MttsHandle* h, const GnParams& g, int B, cudaStream_t stream) {
+  // Bulk-staged 64-row blocks (gn_apply2_kernel) when throughput counts: the launch fills every SM about three times over
+  // (B >= ~80 at T = 344), or the caller keeps several solves in flight on several handles (mtts_set_chains(h, 1)) -- three
+  // B = 64 solves in flight: +2.4 %.  The register-staged kernel (every row requested by its own warp at kernel entry, no
+  // barrier, no TMA round trip) has the shorter chain and wins for ONE small solve at a time (3.83 vs 3.65 M frames/s).
+  const int blocks64 = ((g.Lp + 63) / 64) * B;
+  const bool bulk = h->gn_mode ? h->gn_mode == 2 : (blocks64 >= 3 * h->num_sms || (h->nsub_override == 1 && blocks64 >= h->num_sms));
+  if (bulk) return launch_k(h, gn_apply2_kernel<MODE, 64>, dim3((g.Lp + 63) / 64, B), dim3(GN2_THREADS), gn2_smem_bytes<MODE, 64>(), stream, g);
+  return launch_k(h, gn_apply_kernel<MODE>, dim3((g.Lp + GN_ROWS - 1) / GN_ROWS, B), dim3(GN_THREADS), 0, stream, g);
+}
+
 template <int EPI>
 static int set_gemm_pair_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<256, EPI, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -558,10 +593,32 @@ static int set_gemm_attr() {
   return 0;
 }
 
+// output tensor maps of a 256-wide STATS / PLAIN launch (GemmParams::tma_out); any other launch passes copies of an operand map
+struct OutMaps {
+  CUtensorMap out, res;
+  int on = 0;
+};
+template <int BN, int EPI>
+static int make_out_maps(const MttsHandle* h, OutMaps* o, const CUtensorMap& dummy, const GemmParams& p) {
+  o->out = dummy; o->res = dummy; o->on = 0;
+  if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN)) {
+    if (!h->tma_out || !p.out || (p.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)) return 0;
+    if (make_out_map(&o->out, p.out, (uint64_t)p.M, (uint64_t)p.n_tiles * BN, (uint64_t)p.ldo)) return MTTS_ECUDA;
+    if (EPI == EPI_STATS && p.res_chunk0 > 0) {
+      if (reinterpret_cast<uintptr_t>(p.res_out) & 15) return 0;
+      if (make_out_map(&o->res, p.res_out, (uint64_t)p.M, (uint64_t)p.n_tiles * BN, (uint64_t)p.ldo)) return MTTS_ECUDA;
+    }
+    o->on = 1;
+  }
+  return 0;
+}
+
 template <int BN, int EPI, int KSUB>
 static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& wmap,
                             const GemmParams& p, cudaStream_t stream, double aflops) {
   if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
+  OutMaps om;
+  if (int e = make_out_maps<BN, EPI>(h, &om, a0, p)) return e;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = p.m_major ? m_tiles : m_tiles * p.n_tiles;   // m_major: one CTA per row tile, all its N tiles
   int grid = tiles < h->num_sms ? tiles : h->num_sms;
@@ -572,8 +629,9 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   pp.a_prefetch = h->a_prefetch ? 1 : 0;
   pp.pdl_late = h->pdl_late ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
+  pp.tma_out = om.on;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
-                    wmap, pp));
+                    wmap, om.out, om.res, pp));
   launched(h);
   return 0;
 }
@@ -619,8 +677,11 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
         pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
         const bool t3 = nsrc > 0 && h->pair_tap3;
         pp.tap3 = t3 ? nsrc : 0;
+        OutMaps om;
+        if (int e = make_out_maps<256, EPI>(h, &om, a0.d2, p)) return e;
+        pp.tma_out = om.on;
         CUDA_TRY(launch_k_pair(h, gemm_tc_kernel<256, EPI, 1, 2>, dim3(2 * pairs), dim3(GEMM_THREADS), GemmSmem<256, EPI, 1, 2>::TOTAL,
-                               stream, t3 ? a0.d2t : a0.d2, t3 ? (nsrc == 2 ? a1.d2t : a0.d2t) : a1.d2, wmap.d2h, pp));
+                               stream, t3 ? a0.d2t : a0.d2, t3 ? (nsrc == 2 ? a1.d2t : a0.d2t) : a1.d2, wmap.d2h, om.out, om.res, pp));
         launched(h);
         return 0;
       }
@@ -685,14 +746,13 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     p.n_tiles = 1;
     if (int e = launch_gemm<256, EPI_STATS>(h, in0, in1, sw.m_c1, p, stream, fr * C * 4 * ci_real)) return e;
   }
-  const dim3 gn_grid((lc.Lp + GN_ROWS - 1) / GN_ROWS, w.B);
   // h1 = (Mish(GN(y))*m + temb)*m
   {
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn1_g); g.beta = F(sw.gn1_b); g.rowmask = lc.mask;
     g.temb = te6 + (size_t)s * C; g.t_off = t_off; g.t_stride = t_stride; g.t_ld = 6 * C; g.out = H(w.h1);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_gn<0>(h, g, w.B, stream)); launched(h); }
   }
   // conv2 (k3) -> y, partial sums
   {
@@ -724,7 +784,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lc.L; g.Lp = lc.Lp;
     g.gamma = F(sw.gn2_g); g.beta = F(sw.gn2_b); g.rowmask = lc.mask;
     g.out = H(w.xr); g.res = H(w.res); g.ln_g = F(sw.ln1_g); g.ln_b = F(sw.ln1_b); g.out2 = H(w.a);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<1>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_gn<1>(h, g, w.B, stream)); launched(h); }
   }
   // q | k | v
   if (!h->qkv_gemm) {
@@ -844,8 +904,7 @@ static int run_estimator(MttsHandle* h, Plan& P, int t_off, int t_stride, float*
     GnParams g{};
     g.y = H(w.y); g.stats_part = part; g.S = w.S; g.L = lT.L; g.Lp = lT.Lp;
     g.gamma = F(h->gnf_g); g.beta = F(h->gnf_b); g.rowmask = lT.mask; g.temb = nullptr; g.out = H(w.h1);
-    const dim3 gn_grid((lT.Lp + GN_ROWS - 1) / GN_ROWS, w.B);
-    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_k(h, gn_apply_kernel<0>, gn_grid, dim3(GN_THREADS), 0, stream, g)); launched(h); }
+    if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_gn<0>(h, g, w.B, stream)); launched(h); }
     GemmParams f{};
     f.M = lT.rows; f.rowb = lT.rowb; f.Lp = lT.Lp; f.rowmask = lT.mask; f.mask_mul = 1;
     segs_taps(f, 1, kTap1, C, 0);
@@ -996,6 +1055,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_PAIR_MIN_CHUNKS")) h->pair_min_chunks = atoi(e);
   if (const char* e = getenv("MTTS_NSUB")) h->nsub_override = atoi(e);
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
+  if (const char* e = getenv("MTTS_GN_REGS")) if (e[0] == '1') h->gn_mode = 1;
+  if (const char* e = getenv("MTTS_GN_BULK")) if (e[0] == '1') h->gn_mode = 2;
+  if (const char* e = getenv("MTTS_NO_TMA_OUT")) h->tma_out = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
   if (const char* e = getenv("MTTS_QKV_GEMM")) h->qkv_gemm = (e[0] == '1');
@@ -1022,6 +1084,8 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     if (cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gnb_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(gn_apply2_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn2_smem_bytes<0, 64>()) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(gn_apply2_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn2_smem_bytes<1, 64>()) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(ff_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM) != cudaSuccess) e = 1;
     if (e) { delete h; return fail(MTTS_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: " + g_err); }

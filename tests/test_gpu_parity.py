@@ -447,7 +447,7 @@ def test_chains_setting_keeps_results(lj):
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_PAIRS:one_tile_per_tap", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV",
-                                 "MTTS_QKV_GEMM"])
+                                 "MTTS_QKV_GEMM", "MTTS_GN_REGS", "MTTS_GN_BULK", "MTTS_NO_TMA_OUT"])
 def test_opt_in_variants(env):
     env, _, sub = env.partition(":")
     old = os.environ.get(env)
@@ -549,6 +549,46 @@ def test_fused_gnb_qkv_equals_the_two_launch_path(lj, monkeypatch):
     monkeypatch.setenv("MTTS_GNBQKV", "1")
     dec2, _, _ = U.make_decoder(160)
     for B, T, lengths, seed in [(3, 344, [344, 301, 222], 81), (5, 35, [35, 34, 9, 1, 20], 82), (2, 1024, None, 83)]:
+        mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=seed)
+        za = dec.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
+        zb = dec2.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
+        assert torch.equal(za, zb), (B, T, float((za - zb).abs().max()))
+
+
+def test_bulk_staged_groupnorm_pass_equals_the_register_staged_one(lj, monkeypatch):
+    """gn_apply2_kernel (rows staged through shared memory by one bulk copy per block; chosen for large or concurrent
+    launches, forced here by MTTS_GN_BULK=1) and gn_apply_kernel (MTTS_GN_REGS=1: rows held in registers) run the same
+    arithmetic in the same order: equal to the last bit, over blocks that end inside an utterance, guard rows, ragged
+    masks, odd T and a single-frame utterance."""
+    cfg = lj[1]
+    dev = torch.device("cuda", 0)
+    monkeypatch.setenv("MTTS_GN_BULK", "1")
+    dec, _, _ = U.make_decoder(160)
+    dec._engine(dev)                                   # the switches are read when the native handle is created
+    monkeypatch.delenv("MTTS_GN_BULK")
+    monkeypatch.setenv("MTTS_GN_REGS", "1")
+    dec2, _, _ = U.make_decoder(160)
+    dec2._engine(dev)
+    for B, T, lengths, seed in [(3, 344, [344, 301, 222], 84), (5, 35, [35, 34, 9, 1, 20], 85), (2, 1024, None, 86), (2, 1, None, 87),
+                                (3, 127, [127, 64, 63], 88)]:
+        mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=seed)
+        za = dec.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
+        zb = dec2.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
+        assert torch.equal(za, zb), (B, T, float((za - zb).abs().max()))
+
+
+def test_tma_stored_conv_tiles_equal_the_register_transposed_ones(lj, monkeypatch):
+    """The 256-wide conv / linear tiles leave the epilogue as 32 x 32 TMA boxes by default; MTTS_NO_TMA_OUT=1 restores the
+    shared-memory transpose + st.global.  Same values, same rounding: equal to the last bit (row tiles that end inside the
+    tensor, guard rows, the res_conv half, the ConvTranspose's 512-wide output, odd T)."""
+    cfg = lj[1]
+    dev = torch.device("cuda", 0)
+    dec, _, _ = U.make_decoder(160)
+    dec._engine(dev)                                   # the switch is read when the native handle is created
+    monkeypatch.setenv("MTTS_NO_TMA_OUT", "1")
+    dec2, _, _ = U.make_decoder(160)
+    dec2._engine(dev)
+    for B, T, lengths, seed in [(3, 344, [344, 301, 222], 89), (5, 35, [35, 34, 9, 1, 20], 90), (2, 1024, None, 91), (2, 1, None, 92)]:
         mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=seed)
         za = dec.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
         zb = dec2.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
