@@ -634,6 +634,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
           if (tl && ew == 0 && lane == 0 && c == 0 && ti == 0) tl[11] = clock64();
           if (c + 1 < NCH && !(p.dbg & 4)) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+          if (c + 1 == NCH && !(DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0)) {
+            // this warp's part of the accumulator is in registers: hand the TMEM stage (dual mode: the conv half) back now, not
+            // after the arithmetic, the statistics and the stores of the last chunk -- in dual mode the next tile's conv
+            // chunks wait for exactly this arrive (tools/conv_tiles.py: tile period 5.8 us for 3.8 us of MMAs)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              uint64_t* eb = &tempty_bar[(!DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0) ? 0 : as];
+              if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(eb), 0));
+              else mbar_arrive(eb);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = lds_f4(sp0 + (c * 32 + 4 * j) * 4);
@@ -711,14 +723,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (tl && ew == 0 && lane == 0 && ti == 0) tl[14] = clock64();
         if constexpr (EPI == EPI_STATS) {
           if (p.res_chunk0 > 0) {  // second accumulator: res = acc1 + res_bias (no statistics, no mask)
-            if constexpr (!DUAL_DOUBLE) {   // hand the conv half back, then wait for the res half (see the MMA warp)
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[0]), 0));
-                else mbar_arrive(&tempty_bar[0]);
-                mbar_wait(&tfull_bar[1], aphase);
-              }
+            if constexpr (!DUAL_DOUBLE) {   // the conv half went back above; wait for the res half (see the MMA warp)
+              if (lane == 0) mbar_wait(&tfull_bar[1], aphase);
               __syncwarp();
               tc_fence_after();
             }
@@ -729,6 +735,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               float* v = vbuf[c & 1];
               tmem_ld_wait();
               if (c + 1 < NCH) tmem_ld32(taddr + BN + (c + 1) * 32, vbuf[(c + 1) & 1]);
+              if (c + 1 == NCH) {   // the res half is in registers: hand it back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[DUAL_DOUBLE ? as : 1]), 0));
+                  else mbar_arrive(&tempty_bar[DUAL_DOUBLE ? as : 1]);
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = lds_f4(spar + (256 + n0 + cbase + c * 32 + 4 * j) * 4);
@@ -807,15 +821,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
       if (tl && ew == 0 && lane == 0) tl[6] = clock64();
       if (p.tl2 && ew == 0 && lane == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti + 3] = clock64();
-      // release the accumulator stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
+      // release the accumulator stage back to the MMA warp (STATS / PLAIN did it as soon as the accumulator was in registers)
       const bool dual_split = !DUAL_DOUBLE && epi_has_stats(EPI) && p.res_chunk0 > 0;
-      if (lane == 0) {
-        // dual_split: EPI_STATS released the conv half above and releases the res half here
-        uint64_t* eb = &tempty_bar[dual_split ? 1 : as];
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(eb), 0));   // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(eb);
+      if constexpr (EPI != EPI_STATS && EPI != EPI_PLAIN) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          uint64_t* eb = &tempty_bar[as];
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(eb), 0));   // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(eb);
+        }
       }
       if (dual_split) { aphase ^= 1; }   // dual accumulator, 256-wide: single stage
       else { as ^= 1; if (as == 0) aphase ^= 1; }
