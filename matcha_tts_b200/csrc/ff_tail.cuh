@@ -130,19 +130,21 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     if constexpr (CG == 2) tmem_alloc_pair<512>(tmem_slot);
     else tmem_alloc<512>(tmem_slot);
   }
-  if (warp >= 3) {  // weights-only parameters: staged while the previous kernel drains
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 3) {  // weights-only parameters: staged by the epilogue warps behind their own barrier (gemm_tc.cuh), so that the
+                    // producer's first TMA instructions do not wait for this global-memory round trip
     for (int i = threadIdx.x - 96; i < 256; i += 32 * NEW) {
       s_par[i] = p.b_o[i]; s_par[256 + i] = p.ln_g[i]; s_par[512 + i] = p.ln_b[i]; s_par[768 + i] = p.b2[i];
     }
     for (int i = threadIdx.x - 96; i < 1024; i += 32 * NEW) {
       s_par[1024 + i] = p.b1[i]; s_par[2048 + i] = p.sn_a[i]; s_par[3072 + i] = p.sn_ib[i];
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
   }
-  tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
-  else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const uint32_t tR = tmem_base;
   const uint32_t tD1 = tmem_base + 256;
   const uint32_t tC = tmem_base + 384;

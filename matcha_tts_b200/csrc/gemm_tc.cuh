@@ -296,20 +296,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if constexpr (CG == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
     else tmem_alloc<TMEM_COLS>(tmem_slot);
   }
-  // per-column epilogue parameters (weights: independent of the previous kernel) for every n-tile
-  if (warp >= 3) {
-    const int ncols = min(p.n_tiles * BN, PN);
-    for (int i = threadIdx.x - 96; i < ncols; i += 32 * GEMM_EPI_WARPS) {
-      s_par[i] = p.bias ? p.bias[i] : 0.f;
-      if constexpr (epi_has_stats(EPI)) if (p.res_chunk0 > 0 && i < 256) s_par[256 + i] = p.res_bias[i];  // the conv's own N is 256
-    }
-  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tl && threadIdx.x == 0) tl[1] = clock64();
+  // per-column epilogue parameters (weights: independent of the previous kernel) for every n-tile.  Staged AFTER the block
+  // barrier and closed by a barrier of the epilogue warps alone: their global-memory round trip (~0.6 us) no longer holds
+  // back the producers' first TMA instructions -- with several solves in flight the predecessor has long finished and
+  // every cycle of a CTA's prologue is a cycle its SM does nothing else
+  if (warp >= 3) {
+    const int ncols = min(p.n_tiles * BN, PN);
+    for (int i = threadIdx.x - 96; i < ncols; i += 32 * GEMM_EPI_WARPS) {
+      s_par[i] = p.bias ? p.bias[i] : 0.f;
+      if constexpr (epi_has_stats(EPI)) if (p.res_chunk0 > 0 && i < 256) s_par[256 + i] = p.res_bias[i];  // the conv's own N is 256
+    }
+    epi_bar_sync();
+  }
 
   if (warp == 2) {
     // ===================================== TMA producer: weights (no dependency wait) ==========
@@ -342,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int ti = 0, tile; (tile = cta_tile(ti)) >= 0; ++ti) {
         const int n0 = (tile % p.n_tiles) * BN;
         for (int c = 0; c < CH; ++c)
-          for (int t = 0; t < 3; ++t) put(t * CH + c, n0);
+          for (int t = (p.dbg & 8) ? 2 : 0; t < 3; ++t) put(t * CH + c, n0);
         if (has_res)
           for (int c = 0; c < CH; ++c) put(p.res_chunk0 + c, n0);
       }
@@ -474,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int c = 0; c < CH; ++c) {
           mbar_wait(&afull[sa_i], sa_ph);
           if (p.tl2 && lane == 0 && c == 0 && ti < 16) p.tl2[(size_t)blockIdx.x * 64 + 4 * ti] = clock64();
-          for (int t = 0; t < 3; ++t) {
+          for (int t = (p.dbg & 8) ? 2 : 0; t < 3; ++t) {   // dbg 8: one tap only (timing experiment, wrong results)
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(smem + sa_i * TAP_A_BYTES) + t * (GEMM_BK * 2));
@@ -482,13 +486,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (elect_one()) {
               if constexpr (CG == 2) {
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | (t != ((p.dbg & 8) ? 2 : 0)) | k) != 0);
                 umma_commit_pair(&empty_bar[stage]);
                 if (t == 2) umma_commit_pair(&aempty[sa_i]);
                 if (t == 2 && c + 1 == CH) umma_commit_pair(&tfull_bar[has_res ? 0 : as]);
               } else {
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | (t != ((p.dbg & 8) ? 2 : 0)) | k) != 0);
                 umma_commit(&empty_bar[stage]);
                 if (t == 2) umma_commit(&aempty[sa_i]);
                 if (t == 2 && c + 1 == CH) umma_commit(&tfull_bar[has_res ? 0 : as]);
@@ -836,7 +840,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       else { as ^= 1; if (as == 0) aphase ^= 1; }
     }
     if constexpr (BN == 256 && (EPI == EPI_STATS || EPI == EPI_PLAIN))
-      if (p.tma_out && lane == 0) tma_store_wait<0>();   // the boxes are in global memory before the CTA retires
+      if (p.tma_out && lane == 0) tma_store_wait_read<0>();   // TMA has read the staging tiles before the CTA (and its shared memory) retires;
+                                                              // the writes themselves are ordered by kernel completion
   }
 
   tc_fence_before();

@@ -238,6 +238,7 @@ struct MttsHandle {
   bool w_hint = true;      // weights are loaded with the L2 evict_last hint
   bool tma_out = true;      // 256-wide conv / linear tiles leave the epilogue as 32 x 32 TMA boxes (MTTS_NO_TMA_OUT=1: shared-memory transpose +
                             // st.global, same bits)
+  int dbg = 0;              // MTTS_SOLVE_DBG: GemmParams::dbg for every conv launch of the solve (timing experiments only)
   int gn_mode = 0;          // GroupNorm-apply pass: 0 = by launch size / concurrency (launch_gn), 1 = always the register-staged
                             // gn_apply_kernel (MTTS_GN_REGS=1), 2 = always the bulk-staged gn_apply2_kernel (MTTS_GN_BULK=1); same bits
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
@@ -630,6 +631,7 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   pp.pdl_late = h->pdl_late ? 1 : 0;
   if (h->tl_buf && h->tl_count < h->tl_max) pp.tl = h->tl_buf + (size_t)(h->tl_count++) * 148 * 16;
   pp.tma_out = om.on;
+  if (h->dbg) pp.dbg = h->dbg;
   CUDA_TRY(launch_k(h, gemm_tc_kernel<BN, EPI, KSUB>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, EPI, KSUB>::TOTAL, stream, a0, a1,
                     wmap, om.out, om.res, pp));
   launched(h);
@@ -1057,6 +1059,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_TAP3")) h->tap3 = !(e[0] == '1');
   if (const char* e = getenv("MTTS_GN_REGS")) if (e[0] == '1') h->gn_mode = 1;
   if (const char* e = getenv("MTTS_GN_BULK")) if (e[0] == '1') h->gn_mode = 2;
+  if (const char* e = getenv("MTTS_SOLVE_DBG")) h->dbg = atoi(e);
   if (const char* e = getenv("MTTS_NO_TMA_OUT")) h->tma_out = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
