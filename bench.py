@@ -6,9 +6,10 @@
 A "step" is one full n_timesteps=10 Euler solve of one batch (BASELINE configs[1]: LJSpeech-shape
 decoder, B=64 utterances x T_mel=344 frames, random-init weights, synthetic mu / noise).
   value : whole-job mel-frames/s with inputs resident in HBM (CUDA-graph replay of the solve).  The K steps are K
-          independent batches; `--in-flight F` (default 2) of them are in flight at a time, each on its own solve
-          lane (CUDA stream + native handle), the way a serving process overlaps consecutive batches: one solve is a
-          serial chain of ~490 latency-bound kernels, a second one fills the SMs it leaves idle.  Timed with CUDA
+          independent batches; `--in-flight F` (default 4) of them are in flight at a time, each on its own solve
+          lane (CUDA stream + native handle told about F through mtts_set_lanes: every persistent launch then takes
+          its share of the SMs), the way a serving process overlaps consecutive batches: one solve is a serial chain
+          of ~490 latency-bound kernels whose CTAs get ~1 tile each on 148 SMs.  Timed with CUDA
           events around all K steps, max over ranks; the steps rotate over distinct input sets larger than L2.
           config.serial holds the one-solve-at-a-time figure (L2 flushed between steps), config.sustained the same
           loop over 120 steps (under the power cap).
@@ -598,7 +599,8 @@ def run_native(args):
         with torch.cuda.stream(ls):
             lane_eng.append(dec._engine(dev))                   # one native engine per stream
         if F > 1:
-            lane_eng[-1].set_chains(1)                          # the solves overlap each other: no split inside a solve
+            lane_eng[-1].set_chains(1)                          # the solves overlap each other: no split inside a solve ...
+            lane_eng[-1].set_lanes(F)                           # ... and every persistent launch takes its share of the SMs
         sets = []
         for k in range(NSET):
             gk = torch.Generator().manual_seed(100 + 10 * li + k + 1000 * rank)
@@ -712,6 +714,8 @@ def run_native(args):
     # ---- per-kernel timing of one solve (CUDA events around every launch) for the roofline ----
     roof = None
     kinds = {}
+    if F > 1:
+        eng.set_lanes(1)                                        # each launch below runs alone on the GPU: full grids
     with torch.cuda.stream(stream):
         z.copy_(z0)
         torch.cuda.synchronize(dev)
@@ -852,6 +856,7 @@ def run_native(args):
                 "operands": "fp16 tensors, fp32 accumulate (bf16 operands miss the 1e-3 rel-L2 parity bar; same tensor rate)",
                 "model_tflops_per_gpu": flop_step / (total_ms / args.steps * 1e-3) / 1e12,
                 "in_flight_solves": F, "chains_per_solve": 1 if F > 1 else "heuristic (2)",
+                "sm_share": "mtts_set_lanes(%d): persistent launches sized for 148 * 5/4 / %d SMs at most" % (F, F) if F > 1 else None,
                 "l2": f"steps rotate over {F * NSET} distinct (mu, z0, z) sets = {set_bytes / 2**20:.0f} MiB > 126 MB L2, and every solve "
                       f"streams its own {eng.workspace(B, T)[2] / 2**20:.0f} MiB workspace; the serial figure flushes L2 (256 MiB write) between steps",
                 "sustained": sustained,
@@ -880,7 +885,7 @@ def main():
     ap.add_argument("--frames", type=int, default=344)
     ap.add_argument("--n-timesteps", type=int, default=10)
     ap.add_argument("--ragged", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "3")), help="independent solves (batches) in flight at a time")
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "4")), help="independent solves (batches) in flight at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=120, help="extra timed region of this many steps (0 = skip)")
     ap.add_argument("--no-synthesize", action="store_true", help="skip the tokens -> mel leg (MatchaTTS.synthesise)")
@@ -888,7 +893,7 @@ def main():
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 job folded into the line")
     ap.add_argument("--config5-utts", type=int, default=4096)
     ap.add_argument("--config5-frames", type=int, default=64 * 344, help="padded-frame budget per bucket")
-    ap.add_argument("--config5-lanes", type=int, default=3)
+    ap.add_argument("--config5-lanes", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -106,6 +106,13 @@ int mtts_euler_solve(MttsHandle* h, float* z_inout, const float* mu, const float
  * other instead).  Takes effect for the following mtts_euler_solve / mtts_workspace_bytes calls. */
 int mtts_set_chains(MttsHandle* h, int n);
 
+/* Solves the caller keeps in flight at a time on as many handles / streams (default 1).  With lanes > 1 every persistent
+ * launch of this handle sizes its grid for its share of the SMs (148 x 5/4 / lanes at most, the grid inside that window
+ * with the least wave-quantisation waste) instead of all of them: a batch-64 kernel then runs full waves on ~44 SMs next
+ * to the other lanes' kernels rather than 1.17 tiles per CTA on every SM.  Call it together with mtts_set_chains(h, 1);
+ * results are bit-identical for every value.  Takes effect for the following calls (cached graphs are dropped). */
+int mtts_set_lanes(MttsHandle* h, int lanes);
+
 /* Number of kernels enqueued by the last estimator_forward / euler_solve call on this handle. */
 int mtts_last_launch_count(const MttsHandle* h);
 

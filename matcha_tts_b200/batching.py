@@ -301,6 +301,8 @@ def solve_sharded(mus: Sequence[torch.Tensor], solver: Solver, spks: Optional[Se
     (matcha_tts_b200.CFM); the CPU tests inject a stub, the scheduling/gather logic is the same.
     `lanes` > 1 (CUDA only) keeps that many buckets in flight on as many CUDA streams -- every stream has its own
     native engine, so consecutive solves overlap on the GPU -- and copies the mels to pinned host memory asynchronously.
+    Tell the decoder about it (`decoder.set_lanes(lanes)`): a solve that shares the GPU needs no utterance chains, and its
+    persistent kernels then take their share of the SMs instead of one tile per CTA on all of them (+15 % at four lanes).
     """
     import torch.distributed as dist
     use_dist = dist.is_available() and dist.is_initialized()

@@ -238,6 +238,7 @@ struct MttsHandle {
   bool w_hint = true;      // weights are loaded with the L2 evict_last hint
   bool tma_out = true;      // 256-wide conv / linear tiles leave the epilogue as 32 x 32 TMA boxes (MTTS_NO_TMA_OUT=1: shared-memory transpose +
                             // st.global, same bits)
+  int lanes = 1;            // mtts_set_lanes: solves the caller keeps in flight on as many handles / streams (MTTS_LANES in the environment)
   int dbg = 0;              // MTTS_SOLVE_DBG: GemmParams::dbg for every conv launch of the solve (timing experiments only)
   int gn_mode = 0;          // GroupNorm-apply pass: 0 = by launch size / concurrency (launch_gn), 1 = always the register-staged
                             // gn_apply_kernel (MTTS_GN_REGS=1), 2 = always the bulk-staged gn_apply2_kernel (MTTS_GN_BULK=1); same bits
@@ -567,6 +568,29 @@ static cudaError_t launch_k_pair(const MttsHandle* h, void (*kern)(KArgs...), di
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// Grid of a persistent one-CTA-per-SM launch over `tiles` work units.  One solve at a time: every SM.  With `lanes` solves in
+// flight (mtts_set_lanes) a launch takes its SHARE of the SMs instead: a B = 64 kernel has 173 (level T) or 87 (level T/2)
+// row tiles, i.e. 1.17 / 0.59 tiles per CTA on 148 SMs, and each CTA's fixed time -- prologue, first-operand latency, the
+// last tile's epilogue, exit: ~5 us next to 3.5 us of MMAs per tile -- is SM time no other lane can use.  On 44 SMs the same
+// kernel runs 4 / 2 full waves (the epilogue of tile i under the main loop of tile i + 1, one prologue per 4 tiles) while the
+// other lanes' kernels run next to it: 4.98 -> 5.7-5.9 M mel-frames/s with four lanes (profiles/r05n_sm_share_sweep.txt).
+// The share may be oversubscribed by up to a quarter (kernels of different lanes rarely all peak together: 44 x 4 = 176);
+// inside that window the grid with the least wave-quantisation waste wins (43 CTAs for 173 tiles = 5 waves: -6 %).
+static int lane_grid(const MttsHandle* h, int tiles, int ctas_per_sm = 1) {
+  const int all = h->num_sms * ctas_per_sm;
+  if (h->lanes <= 1 || tiles <= 0) return tiles < all ? tiles : all;
+  const int lo = (all + h->lanes - 1) / h->lanes, hi = (all * 5 / 4 + h->lanes - 1) / h->lanes;
+  if (tiles <= lo) return tiles;
+  int best = lo;
+  double best_w = 1e30;
+  for (int g = lo; g <= hi && g <= all; ++g) {
+    const int waves = (tiles + g - 1) / g;
+    const double w = (double)waves * g / tiles;
+    if (w < best_w * 0.99 || (w <= best_w * 1.0001 && g > best)) { if (w < best_w) best_w = w; best = g; }
+  }
+  return best < tiles ? best : tiles;
+}
+
 // GroupNorm-apply pass (elementwise.cuh): rows staged by one bulk copy per block, or the register-staged form
 template <int MODE>
 static cudaError_t launch_gn(const MttsHandle* h, const GnParams& g, int B, cudaStream_t stream) {
@@ -622,7 +646,7 @@ static int launch_gemm_maps(MttsHandle* h, const CUtensorMap& a0, const CUtensor
   if (int e = make_out_maps<BN, EPI>(h, &om, a0, p)) return e;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = p.m_major ? m_tiles : m_tiles * p.n_tiles;   // m_major: one CTA per row tile, all its N tiles
-  int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  int grid = lane_grid(h, tiles);
   GemmParams pp = p;
   pp.tl = nullptr;
   pp.tl2 = h->tl2_buf;
@@ -775,7 +799,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       gp.q = H(w.q); gp.k = H(w.k); gp.v = H(w.v); gp.w_hint = h->w_hint ? 1 : 0; gp.pdl_late = h->pdl_late ? 1 : 0;
       gp.tl = h->tail_tl;   // debug stamps share the tail kernel's buffer (tools/gq_timeline.py stops before the first tail launch)
       const int tiles = (lc.rows + 127) / 128;
-      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+      const int grid = lane_grid(h, tiles);
       CUDA_TRY(launch_k(h, gnb_qkv_kernel, dim3(grid), dim3(GQ_THREADS), GQ_SMEM, stream, sw.m_qkv.d2, gp));
       launched(h);
     }
@@ -795,7 +819,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       qp.M = lc.rows; qp.q = H(w.q); qp.k = H(w.k); qp.v = H(w.v); qp.w_hint = h->w_hint ? 1 : 0; qp.pdl_late = h->pdl_late ? 1 : 0;
       qp.tl = h->tail_tl;   // debug stamps share the tail kernel's buffer (tools/qkv_timeline.py stops before the first tail launch)
       const int tiles = (lc.rows + 127) / 128;
-      const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+      const int grid = lane_grid(h, tiles);
       CUDA_TRY(launch_k(h, qkv_kernel, dim3(grid), dim3(QKV_THREADS), QKV_SMEM, stream, lm.a.d2, sw.m_qkv.d2, qp));
       launched(h);
     }
@@ -809,7 +833,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
     const int items = ((lc.L + 127) / 128) * 2 * w.B;
-    dim3 grid(items < 2 * h->num_sms ? items : 2 * h->num_sms);   // persistent: two CTAs per SM walk the (query tile, head, utterance) items
+    dim3 grid(lane_grid(h, items, 2));   // persistent: two CTAs per SM walk the (query tile, head, utterance) items
     Attn2Params ap{};
     ap.B = w.B;
     ap.L = lc.L; ap.Lp = lc.Lp; ap.KT = lm.KT; ap.nkv = lm.nkv; ap.rowmask = lc.mask; ap.npad = lc.npad;
@@ -825,7 +849,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     tp.rowmask = lc.mask; tp.out = out; tp.w_hint = h->w_hint ? 1 : 0; tp.pdl_late = h->pdl_late ? 1 : 0;
     tp.tl = h->tail_tl;
     const int tiles = (lc.rows + 127) / 128;
-    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    const int grid = lane_grid(h, tiles);
     if (h->tail_pairs) {
       const int units = (tiles + 1) / 2;
       const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
@@ -1080,6 +1104,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
       return fail(MTTS_ECUDA, "this library contains sm_100a code only; device is not Blackwell (cc 10.x)");
     }
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e2 = getenv("MTTS_LANES")) { const int n = atoi(e2); if (n >= 1 && n <= 16) h->lanes = n; }
     int e = 0;
     e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>();
@@ -1346,13 +1371,27 @@ int mtts_set_chains(MttsHandle* h, int n) {
   if (!h) return fail(MTTS_EINVAL, "null handle");
   if (n < 0 || n > 8) return fail(MTTS_EINVAL, "chains must be in [0, 8]");
   if (n != h->nsub_override) {   // the captured graphs embed the chain structure, the plans the chain partition
-    DEVICE_GUARD(h);
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
-    h->graphs.clear();
+    if (!h->graphs.empty()) {
+      DEVICE_GUARD(h);
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+      h->graphs.clear();
+    }
     h->plans.clear();
     h->ws_nsub.clear();
   }
   h->nsub_override = n;
+  return 0;
+}
+
+int mtts_set_lanes(MttsHandle* h, int lanes) {
+  if (!h) return fail(MTTS_EINVAL, "null handle");
+  if (lanes < 1 || lanes > 16) return fail(MTTS_EINVAL, "lanes must be in [1, 16]");
+  if (lanes != h->lanes && !h->graphs.empty()) {   // the captured graphs embed the launch grids
+    DEVICE_GUARD(h);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    h->graphs.clear();
+  }
+  h->lanes = lanes;
   return 0;
 }
 

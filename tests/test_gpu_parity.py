@@ -593,3 +593,21 @@ def test_tma_stored_conv_tiles_equal_the_register_transposed_ones(lj, monkeypatc
         za = dec.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
         zb = dec2.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
         assert torch.equal(za, zb), (B, T, float((za - zb).abs().max()))
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 7])
+def test_sm_share_of_concurrent_solves_changes_no_bit(lj, lanes):
+    """Decoder.set_lanes(n) (mtts_set_lanes): persistent launches sized for their share of the SMs -- fewer, longer-lived CTAs
+    walking the same tiles.  Every tile is computed by the same code in the same order: equal to the last bit, eager and
+    through the CUDA graph, also when a launch has fewer tiles than its share (B = 2) or many more (T = 1024)."""
+    cfg = lj[1]
+    dec, _, _ = U.make_decoder(160)
+    dec.set_chains(1)
+    dec2, _, _ = U.make_decoder(160)
+    dec2.set_lanes(lanes)
+    for B, T, lengths, seed in [(64, 344, None, 97), (2, 344, [344, 200], 98), (3, 1024, [1024, 700, 33], 99)]:
+        mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=seed)
+        for use_graph in (False, True):
+            za = dec.solve(_d(z0), _d(mu), _d(mask), 2, None, "euler", use_graph=use_graph)
+            zb = dec2.solve(_d(z0), _d(mu), _d(mask), 2, None, "euler", use_graph=use_graph)
+            assert torch.equal(za, zb), (lanes, B, T, use_graph, float((za - zb).abs().max()))

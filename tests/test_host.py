@@ -35,6 +35,23 @@ def test_header_symbols_exported(libmtts):
     assert b"sm_100a" in libmtts.mtts_version()
 
 
+def test_lanes_and_chains_switches_validate_their_argument(libmtts):
+    """mtts_set_lanes / mtts_set_chains (include/mtts.h): range-checked, no GPU needed."""
+    from matcha_tts_b200 import _lib
+    cfg = _lib.MttsConfig(160, 80, 256, 2, 64, 2)
+    h = C.c_void_p()
+    _lib.check(libmtts.mtts_create(C.byref(cfg), 0, C.byref(h)))
+    try:
+        for n in (1, 4, 16):
+            assert libmtts.mtts_set_lanes(h, n) == 0
+        for n in (0, -1, 17):
+            assert libmtts.mtts_set_lanes(h, n) < 0
+        assert libmtts.mtts_set_lanes(None, 2) < 0
+        assert libmtts.mtts_set_chains(h, 9) < 0 and libmtts.mtts_set_chains(h, 1) == 0
+    finally:
+        libmtts.mtts_destroy(h)
+
+
 @pytest.mark.parametrize("cin", [160, 224])
 def test_weight_table_matches_state_dict(libmtts, cin):
     from matcha_tts_b200 import _lib

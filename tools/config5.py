@@ -19,14 +19,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=3, passes=3, with_hash=True):
+def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=4, passes=3, with_hash=True):
     from matcha_tts_b200 import CFM, Decoder, batching
     import torch.distributed as dist
     g = torch.Generator().manual_seed(6)
     lengths = torch.exp(torch.randn(n_utt, generator=g) * 0.45 + 5.7).clamp(64, 800).long().tolist()   # median ~300
     torch.manual_seed(0)
     dec = Decoder(in_channels=224, out_channels=80, channels=(256, 256), num_heads=2, num_mid_blocks=2).to(dev)
-    dec.set_chains(1)
+    dec.set_lanes(lanes)                  # `lanes` buckets in flight: no split inside a solve, every launch takes its share of the SMs
     cfm = CFM(80, {"solver": "euler", "sigma_min": 1e-4}, n_spks=109, spk_emb_dim=64, estimator=dec)
     gd = torch.Generator(device=dev).manual_seed(5)
     mus = [torch.randn(80, n, generator=gd, device=dev) for n in lengths]
@@ -99,7 +99,7 @@ def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=3, passes=3, wi
 def main():
     n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     max_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64 * 344
-    lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 4
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
