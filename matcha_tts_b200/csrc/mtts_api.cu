@@ -243,7 +243,8 @@ struct MttsHandle {
   int gn_mode = 0;          // GroupNorm-apply pass: 0 = by launch size / concurrency (launch_gn), 1 = always the register-staged
                             // gn_apply_kernel (MTTS_GN_REGS=1), 2 = always the bulk-staged gn_apply2_kernel (MTTS_GN_BULK=1); same bits
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
-  bool tail_pairs = false;  // MTTS_TAIL_PAIRS=1: ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA)
+  bool tail_pairs = true;   // ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA); MTTS_TAIL_PAIRS=0:
+                            // one CTA per row tile.  On by default since the lanes own their SMs (mtts_set_lanes): see cta_pairs
   bool qkv_gemm = false;    // MTTS_QKV_GEMM=1: the QKV projection through the generic gemm_tc_kernel<128, EPI_QKV> (one unit per N tile,
                             // the activation tile staged three times) instead of qkv_kernel (qkv.cuh)
   bool fused_gnb = false;   // MTTS_GNBQKV=1: gnb_qkv_kernel (GroupNorm-apply + residual + LayerNorm1 + QKV GEMM in one launch, 43 instead of 49
@@ -252,10 +253,14 @@ struct MttsHandle {
                             // solve at a time (3.55 vs 3.75 M frames/s): its transform runs on 8 warps per SM at ~0.4 IPC per scheduler
                             // partition while the stand-alone pass has ~40 warps per SM -- profiles/r02_gnbqkv_*.txt
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
-  int pair_min_chunks = 24;  // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM
+  int pair_min_chunks = 9;   // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM (9 = the first conv)
   bool pair_tap3 = true;  // CTA pairs use tap sharing as well (MTTS_PAIR_TAP3=0: one activation tile per tap, the round-1 pair kernel)
-  bool cta_pairs = false; // MTTS_PAIRS=1: 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2).  Off: in the solve the
-                          // pair launches measured -1% (4.57 vs 4.63 M frames/s) although the kernel alone gains 5-10% at full occupancy
+  bool cta_pairs = true;  // 256-wide conv GEMMs with K >= pair_min_chunks on CTA pairs (cta_group::2) with tap sharing; MTTS_PAIRS=0: single CTAs.
+                          // Alone the pair kernels were always faster (main loop 2.5-2.9 us per 256 rows against 3.5-3.8 us per 128), but
+                          // with several solves sharing ALL SMs their cluster launches lost that again (-1 %: both SMs of a TPC must be
+                          // free at once).  Since every lane runs on its own share of the SMs (mtts_set_lanes) they pay: +4 % with four
+                          // solves in flight, +1.3 % for one solve at a time, and less power per FLOP (sustained +3.7 %) --
+                          // profiles/r05q_pairs_under_lanes.txt
   bool pdl_late = true;  // GEMM / tail / attention CTAs release their dependents (griddepcontrol.launch_dependents) when their last
                          // accumulator is complete, not at kernel entry: dependents released at entry sit
                          // on SM slots (shared memory, TMEM) that ready kernels of another chain / solve could use (+4.5% with three
@@ -697,7 +702,7 @@ static int launch_gemm(MttsHandle* h, const TMap& a0, const TMap& a1, const TMap
         if (!can_launch(h, MTTS_KIND_GEMM, aflops)) return 0;
         const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
         const int units = ((m_tiles + 1) / 2) * p.n_tiles;
-        const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+        const int pairs = (lane_grid(h, 2 * units) + 1) / 2;   // CTA pairs inside this lane's share of the SMs
         GemmParams pp = p;
         pp.tl = nullptr; pp.tl2 = h->tl2_buf; pp.m_major = 0;
         pp.w_hint = h->w_hint ? 1 : 0; pp.a_prefetch = h->a_prefetch ? 1 : 0; pp.pdl_late = h->pdl_late ? 1 : 0;
@@ -852,7 +857,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     const int grid = lane_grid(h, tiles);
     if (h->tail_pairs) {
       const int units = (tiles + 1) / 2;
-      const int pairs = units < h->num_sms / 2 ? units : h->num_sms / 2;
+      const int pairs = (lane_grid(h, 2 * units) + 1) / 2;   // CTA pairs inside this lane's share of the SMs
       CUDA_TRY(launch_k_pair(h, ff_tail_kernel<2>, dim3(2 * pairs), dim3(TAIL_THREADS), TAIL_SMEM, stream, lm.o3, sw.m_wo_h, sw.t_ff1_h,
                              sw.m_ff2_h, tp));
     } else {

@@ -446,16 +446,16 @@ def test_chains_setting_keeps_results(lj):
 # ---------------------------------------------------------------------------------------------
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env", ["MTTS_NO_PDL", "MTTS_PAIRS", "MTTS_PAIRS:one_tile_per_tap", "MTTS_TAIL_PAIRS", "MTTS_NO_TAP3", "MTTS_GNBQKV",
-                                 "MTTS_QKV_GEMM", "MTTS_GN_REGS", "MTTS_GN_BULK", "MTTS_NO_TMA_OUT"])
+@pytest.mark.parametrize("env", ["MTTS_NO_PDL=1", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0,MTTS_PAIR_TAP3=0",
+                                 "MTTS_PAIRS=0", "MTTS_TAIL_PAIRS=0", "MTTS_PAIRS=0,MTTS_TAIL_PAIRS=0", "MTTS_NO_TAP3=1,MTTS_PAIRS=0", "MTTS_GNBQKV=1",
+                                 "MTTS_QKV_GEMM=1", "MTTS_GN_REGS=1", "MTTS_GN_BULK=1", "MTTS_NO_TMA_OUT=1", "MTTS_LANES=4"])
 def test_opt_in_variants(env):
-    env, _, sub = env.partition(":")
-    old = os.environ.get(env)
-    os.environ[env] = "1"
-    if env == "MTTS_PAIRS":
-        os.environ["MTTS_PAIR_MIN_CHUNKS"] = "0"
-        if sub:                      # the CTA-pair GEMM without tap sharing (one activation tile per tap)
-            os.environ["MTTS_PAIR_TAP3"] = "0"
+    """Every switch the library reads at handle creation, alone and in the combinations that select a
+    different kernel, stays inside the parity bar."""
+    pairs = [kv.split("=") for kv in env.split(",")]
+    old = {k: os.environ.get(k) for k, _ in pairs}
+    for k, v in pairs:
+        os.environ[k] = v
     try:
         dec, cfg, sd = U.make_decoder(160)
         mu, mask, z0, _ = O.make_inputs(cfg, 3, 344, [344, 301, 222], seed=80)
@@ -464,17 +464,16 @@ def test_opt_in_variants(env):
             z = dec.solve(_d(z0), _d(mu), _d(mask), 4, None, "euler", use_graph=use_graph).cpu()
             ma, rl = O.parity_errors(z, zr, mask)
             assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (env, use_graph, ma, rl)
-        if env == "MTTS_PAIRS":      # the unit GEMM through the CTA-pair kernel: odd tile counts, several N tiles
+        if env.startswith("MTTS_PAIRS=1"):      # the unit GEMM through the CTA-pair kernel: odd tile counts, several N tiles
             eng = dec._engine(torch.device("cuda", 0))
             for rows, Cc, N, shifts in [(129, 256, 256, [-1, 0, 1]), (5000, 256, 1024, [0]), (777, 512, 512, [-1, 0, 1])]:
                 _check_gemm(eng, rows, Cc, N, shifts)
     finally:
-        os.environ.pop("MTTS_PAIR_MIN_CHUNKS", None)
-        os.environ.pop("MTTS_PAIR_TAP3", None)
-        if old is None:
-            os.environ.pop(env, None)
-        else:
-            os.environ[env] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 # ---------------------------------------------------------------------------------------------
