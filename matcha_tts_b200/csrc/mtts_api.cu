@@ -143,8 +143,8 @@ struct TMap {
 };
 static int make_tmap(TMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
   if (make_map(&m->d2, base, rows, cols, pitch, box_rows)) return MTTS_ECUDA;
-  m->d2h = m->d2;
-  if (box_rows == 256 && make_map(&m->d2h, base, rows, cols, pitch, 128)) return MTTS_ECUDA;
+  m->d2h = m->d2;   // half boxes: a CTA pair's share of a weight tile (256-row conv tiles, 128-row QKV pieces)
+  if ((box_rows == 256 || box_rows == 128) && make_map(&m->d2h, base, rows, cols, pitch, box_rows / 2)) return MTTS_ECUDA;
   m->d2t = m->d2;
   if (box_rows == 128 && make_map(&m->d2t, base, rows, cols, pitch, 130)) return MTTS_ECUDA;
   m->d3 = m->d2;
@@ -243,6 +243,7 @@ struct MttsHandle {
   int gn_mode = 0;          // GroupNorm-apply pass: 0 = by launch size / concurrency (launch_gn), 1 = always the register-staged
                             // gn_apply_kernel (MTTS_GN_REGS=1), 2 = always the bulk-staged gn_apply2_kernel (MTTS_GN_BULK=1); same bits
   bool tap3 = true;         // single-source k3 convs stage one 130-row activation tile per K chunk for all three taps (MTTS_NO_TAP3=1: one tile per tap)
+  bool qkv_pairs = true;    // qkv_kernel<2>: the QKV projection on CTA pairs (MTTS_QKV_PAIRS=0: one CTA per row tile)
   bool tail_pairs = true;   // ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA); MTTS_TAIL_PAIRS=0:
                             // one CTA per row tile.  On by default since the lanes own their SMs (mtts_set_lanes): see cta_pairs
   bool qkv_gemm = false;    // MTTS_QKV_GEMM=1: the QKV projection through the generic gemm_tc_kernel<128, EPI_QKV> (one unit per N tile,
@@ -824,8 +825,13 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       qp.M = lc.rows; qp.q = H(w.q); qp.k = H(w.k); qp.v = H(w.v); qp.w_hint = h->w_hint ? 1 : 0; qp.pdl_late = h->pdl_late ? 1 : 0;
       qp.tl = h->tail_tl;   // debug stamps share the tail kernel's buffer (tools/qkv_timeline.py stops before the first tail launch)
       const int tiles = (lc.rows + 127) / 128;
-      const int grid = lane_grid(h, tiles);
-      CUDA_TRY(launch_k(h, qkv_kernel, dim3(grid), dim3(QKV_THREADS), QKV_SMEM, stream, lm.a.d2, sw.m_qkv.d2, qp));
+      if (h->qkv_pairs) {   // a CTA pair per 256 rows, each CTA staging half of every weight piece
+        const int pairs = (lane_grid(h, 2 * ((tiles + 1) / 2)) + 1) / 2;
+        CUDA_TRY(launch_k_pair(h, qkv_kernel<2>, dim3(2 * pairs), dim3(QKV_THREADS), QKV_SMEM, stream, lm.a.d2, sw.m_qkv.d2h, qp));
+      } else {
+        const int grid = lane_grid(h, tiles);
+        CUDA_TRY(launch_k(h, qkv_kernel<1>, dim3(grid), dim3(QKV_THREADS), QKV_SMEM, stream, lm.a.d2, sw.m_qkv.d2, qp));
+      }
       launched(h);
     }
   } else {
@@ -1091,6 +1097,7 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_SOLVE_DBG")) h->dbg = atoi(e);
   if (const char* e = getenv("MTTS_NO_TMA_OUT")) h->tma_out = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
+  if (const char* e = getenv("MTTS_QKV_PAIRS")) h->qkv_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
   if (const char* e = getenv("MTTS_QKV_GEMM")) h->qkv_gemm = (e[0] == '1');
   build_tables(h);
@@ -1114,7 +1121,8 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>();
     e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
-    if (cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(qkv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
+    if (cudaFuncSetAttribute(qkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gnb_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gn_apply2_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn2_smem_bytes<0, 64>()) != cudaSuccess) e = 1;

@@ -447,7 +447,7 @@ def test_chains_setting_keeps_results(lj):
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", ["MTTS_NO_PDL=1", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0,MTTS_PAIR_TAP3=0",
-                                 "MTTS_PAIRS=0", "MTTS_TAIL_PAIRS=0", "MTTS_PAIRS=0,MTTS_TAIL_PAIRS=0", "MTTS_NO_TAP3=1,MTTS_PAIRS=0", "MTTS_GNBQKV=1",
+                                 "MTTS_PAIRS=0", "MTTS_TAIL_PAIRS=0", "MTTS_QKV_PAIRS=0", "MTTS_PAIRS=0,MTTS_TAIL_PAIRS=0,MTTS_QKV_PAIRS=0", "MTTS_NO_TAP3=1,MTTS_PAIRS=0", "MTTS_GNBQKV=1",
                                  "MTTS_QKV_GEMM=1", "MTTS_GN_REGS=1", "MTTS_GN_BULK=1", "MTTS_NO_TMA_OUT=1", "MTTS_LANES=4"])
 def test_opt_in_variants(env):
     """Every switch the library reads at handle creation, alone and in the combinations that select a
