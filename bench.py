@@ -6,7 +6,7 @@
 A "step" is one full n_timesteps=10 Euler solve of one batch (BASELINE configs[1]: LJSpeech-shape
 decoder, B=64 utterances x T_mel=344 frames, random-init weights, synthetic mu / noise).
   value : whole-job mel-frames/s with inputs resident in HBM (CUDA-graph replay of the solve).  The K steps are K
-          independent batches; `--in-flight F` (default 4) of them are in flight at a time, each on its own solve
+          independent batches; `--in-flight F` (default 5) of them are in flight at a time, each on its own solve
           lane (CUDA stream + native handle told about F through mtts_set_lanes: every persistent launch then takes
           its share of the SMs), the way a serving process overlaps consecutive batches: one solve is a serial chain
           of ~490 latency-bound kernels whose CTAs get ~1 tile each on 148 SMs.  Timed with CUDA
@@ -885,7 +885,7 @@ def main():
     ap.add_argument("--frames", type=int, default=344)
     ap.add_argument("--n-timesteps", type=int, default=10)
     ap.add_argument("--ragged", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "4")), help="independent solves (batches) in flight at a time")
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("MTTS_BENCH_INFLIGHT", "5")), help="independent solves (batches) in flight at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=120, help="extra timed region of this many steps (0 = skip)")
     ap.add_argument("--no-synthesize", action="store_true", help="skip the tokens -> mel leg (MatchaTTS.synthesise)")
@@ -893,7 +893,7 @@ def main():
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 job folded into the line")
     ap.add_argument("--config5-utts", type=int, default=4096)
     ap.add_argument("--config5-frames", type=int, default=64 * 344, help="padded-frame budget per bucket")
-    ap.add_argument("--config5-lanes", type=int, default=4)
+    ap.add_argument("--config5-lanes", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

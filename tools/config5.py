@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=4, passes=3, with_hash=True):
+def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=5, passes=3, with_hash=True):
     from matcha_tts_b200 import CFM, Decoder, batching
     import torch.distributed as dist
     g = torch.Generator().manual_seed(6)
@@ -99,7 +99,7 @@ def run(dev, world, rank, n_utt=4096, max_frames=64 * 344, lanes=4, passes=3, wi
 def main():
     n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     max_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64 * 344
-    lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
