@@ -415,7 +415,9 @@ def test_concurrent_lanes_match_serial(lj):
     lanes = [torch.cuda.Stream() for _ in ins]
     torch.cuda.synchronize()
     outs = [None] * len(ins)
-    for rep in range(2):                      # second round replays the lanes' cached graphs
+    for rep in range(4):                      # second round replays the lanes' cached graphs
+        if rep == 2:
+            dec.set_lanes(len(lanes))         # rounds 3 and 4: every lane's persistent launches on its share of the SMs
         for i, (ls, (mu, mask, z0, _)) in enumerate(zip(lanes, ins)):
             ls.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ls):
@@ -424,6 +426,8 @@ def test_concurrent_lanes_match_serial(lj):
         for a, b in zip(serial, outs):
             assert torch.equal(a, b)          # a lane changes nothing but the stream
     assert len({id(e) for e in dec._engines.values()}) >= 4   # default stream + three lanes
+    dec.set_lanes(1)                          # the fixture is shared
+    dec.set_chains(0)
 
 
 def test_chains_setting_keeps_results(lj):
