@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libmtts.so")
 SOURCES = ["mtts_api.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gnb_qkv.cuh", "qkv.cuh", "attention3.cuh", "elementwise.cuh", "ff_tail.cuh", "text_encoder.cuh", "mtts_text.inc", "vocoder.cuh", "stft.cuh", "mtts_voc.inc"]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "qkv.cuh", "attention3.cuh", "elementwise.cuh", "ff_tail.cuh", "text_encoder.cuh", "mtts_text.inc", "vocoder.cuh", "stft.cuh", "mtts_voc.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-ftz=true", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
 // cp.async.bulk for its whole 32 KB slab of y (and of res, MODE 1) the moment the previous kernel has completed, finalises
 // the statistics and fetches its per-row operands while the bytes fly, and then streams the rows out of shared memory:
 // 32-64 KB in flight per block and several blocks per SM, no registers tied up.  The arithmetic is gn_apply_kernel's,
-// operation for operation (same bits; gnb_qkv_kernel relies on that too).
+// operation for operation (same bits).
 // grid = (ceil(Lp / GN2_ROWS), B), block = 256 (8 warps x GN2_ROWS / 8 rows, 8 channels per lane).  Which of the two kernels a
 // launch gets is decided in mtts_api.cu::launch_gn (this one where throughput counts, the register-staged one for one small
 // solve at a time: its chain is shorter -- no barrier, no TMA round trip; 32-row blocks measured between the two)

@@ -28,7 +28,6 @@
 //   EPI_STATS  +bias, fp16 store, deterministic GroupNorm partial sums per (utterance, group); optionally a
 //              second accumulator fed by extra K chunks of the same A tiles (the ResnetBlock1D 1x1 res_conv)
 //   EPI_PLAIN  +bias (+residual) (*row mask), fp16 store
-//   EPI_QKV    q | k | v row-major per head for the attention kernel
 //   EPI_FINAL  final 1x1 projection * mask, Euler update of the fp32 state z (channels-first) and
 //              refresh of the z channels of the first conv's operand buffer
 #pragma once
@@ -47,7 +46,7 @@ constexpr int GEMM_THREADS = 96 + 32 * GEMM_EPI_WARPS;        // 352: A producer
 constexpr int GEMM_MAX_SEGS = 9;
 constexpr int GEMM_STAGING_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 32 fp16, swizzled
 
-enum { EPI_STATS = 0, EPI_PLAIN = 1, EPI_QKV = 4, EPI_FINAL = 5 };
+enum { EPI_STATS = 0, EPI_PLAIN = 1, EPI_FINAL = 5 };
 __host__ __device__ constexpr bool epi_has_stats(int e) { return e == EPI_STATS; }
 
 struct GemmSeg {
@@ -80,10 +79,6 @@ struct GemmParams {
   int res_chunk0;       // 0 = no second GEMM
   const float* res_bias;
   __half* res_out;      // [row*ldo + n]
-  // EPI_QKV
-  __half* q;
-  __half* k;
-  __half* v;   // [rows][128] row-major like q / k
   // EPI_FINAL
   float* zout;         // (B, n_valid, T) channels-first fp32
   const float* zbase;  // same layout or null
@@ -755,21 +750,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               if (tma_out) epi_store_h32_tma(st, lane, v, &tmRes, n0 + cbase + c * 32, rw0, rows_valid);
               else epi_store_h32(st, lane, v, rob + c * 32, p.ldo, rows_valid);
             }
-          }
-        }
-      } else if constexpr (EPI == EPI_QKV) {
-        if (lane == 0) { mbar_wait(&tfull_bar[as], aphase); if (last_tile) pdl_launch_dependents(); }
-        __syncwarp();
-        tc_fence_after();
-        if (tl && ew == 0 && lane == 0 && ti == 0) tl[5] = clock64();
-        {
-          __half* dst = (n_tile == 0 ? p.q : (n_tile == 1 ? p.k : p.v)) + (size_t)rw0 * BN + cbase;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-            epi_store_h32(st, lane, v, dst + c * 32, BN, rows_valid);
           }
         }
       } else {  // EPI_FINAL

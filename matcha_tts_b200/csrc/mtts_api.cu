@@ -18,7 +18,6 @@
 #include "elementwise.cuh"
 #include "ff_tail.cuh"
 #include "gemm_tc.cuh"
-#include "gnb_qkv.cuh"
 #include "qkv.cuh"
 
 using namespace mtts;
@@ -246,13 +245,6 @@ struct MttsHandle {
   bool qkv_pairs = true;    // qkv_kernel<2>: the QKV projection on CTA pairs (MTTS_QKV_PAIRS=0: one CTA per row tile)
   bool tail_pairs = true;   // ff_tail_kernel<2> (cta_group::2, two row tiles per CTA pair, half of every weight piece per CTA); MTTS_TAIL_PAIRS=0:
                             // one CTA per row tile.  On by default since the lanes own their SMs (mtts_set_lanes): see cta_pairs
-  bool qkv_gemm = false;    // MTTS_QKV_GEMM=1: the QKV projection through the generic gemm_tc_kernel<128, EPI_QKV> (one unit per N tile,
-                            // the activation tile staged three times) instead of qkv_kernel (qkv.cuh)
-  bool fused_gnb = false;   // MTTS_GNBQKV=1: gnb_qkv_kernel (GroupNorm-apply + residual + LayerNorm1 + QKV GEMM in one launch, 43 instead of 49
-                            // launches per evaluation) instead of the GroupNorm-apply pass followed by the QKV GEMM launch.  Bit-identical;
-                            // measured equal at full occupancy (70 vs 73 us at level T, 46 vs 45 us at level T/2, B=256) and slower for one
-                            // solve at a time (3.55 vs 3.75 M frames/s): its transform runs on 8 warps per SM at ~0.4 IPC per scheduler
-                            // partition while the stand-alone pass has ~40 warps per SM -- profiles/r02_gnbqkv_*.txt
   bool use_pdl = true;  // MTTS_NO_PDL=1 in the environment disables programmatic dependent launch
   int pair_min_chunks = 9;   // MTTS_PAIR_MIN_CHUNKS: shortest K (in 64-column chunks) that goes to the CTA-pair GEMM (9 = the first conv)
   bool pair_tap3 = true;  // CTA pairs use tap sharing as well (MTTS_PAIR_TAP3=0: one activation tile per tap, the round-1 pair kernel)
@@ -794,22 +786,6 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     p.n_tiles = 1;
     if (int e = launch_gemm<256, EPI_STATS>(h, lm.h1, lm.h1, sw.m_c2, p, stream, fr * C * 3 * C)) return e;
   }
-  if (h->fused_gnb) {
-    // x_r = Mish(GN(y))*m + res ; a = LN1(x_r) (on chip) ; q | k | v = a Wqkv^T   -- one kernel (gnb_qkv.cuh)
-    if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
-      GnbQkvParams gp{};
-      gp.M = lc.rows; gp.L = lc.L; gp.Lp = lc.Lp; gp.S = w.S;
-      gp.y = H(w.y); gp.res = H(w.res); gp.stats_part = part;
-      gp.gamma = F(sw.gn2_g); gp.beta = F(sw.gn2_b); gp.ln_g = F(sw.ln1_g); gp.ln_b = F(sw.ln1_b);
-      gp.rowmask = lc.mask; gp.rowb = lc.rowb; gp.xr = H(w.xr);
-      gp.q = H(w.q); gp.k = H(w.k); gp.v = H(w.v); gp.w_hint = h->w_hint ? 1 : 0; gp.pdl_late = h->pdl_late ? 1 : 0;
-      gp.tl = h->tail_tl;   // debug stamps share the tail kernel's buffer (tools/gq_timeline.py stops before the first tail launch)
-      const int tiles = (lc.rows + 127) / 128;
-      const int grid = lane_grid(h, tiles);
-      CUDA_TRY(launch_k(h, gnb_qkv_kernel, dim3(grid), dim3(GQ_THREADS), GQ_SMEM, stream, sw.m_qkv.d2, gp));
-      launched(h);
-    }
-  } else {
   // x_r = Mish(GN(y))*m + res ; a = LN1(x_r)
   {
     GnParams g{};
@@ -819,7 +795,7 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
     if (can_launch(h, MTTS_KIND_NORM)) { CUDA_TRY(launch_gn<1>(h, g, w.B, stream)); launched(h); }
   }
   // q | k | v
-  if (!h->qkv_gemm) {
+  {
     if (can_launch(h, MTTS_KIND_GEMM, fr * 384 * C)) {
       QkvParams qp{};
       qp.M = lc.rows; qp.q = H(w.q); qp.k = H(w.k); qp.v = H(w.v); qp.w_hint = h->w_hint ? 1 : 0; qp.pdl_late = h->pdl_late ? 1 : 0;
@@ -834,12 +810,6 @@ static int run_stage(MttsHandle* h, Plan& P, int s, const LevelCtx& lc, const TM
       }
       launched(h);
     }
-  } else {
-    GemmParams p = base;
-    segs_taps(p, 1, kTap1, C, 0);
-    p.n_tiles = 3; p.bias = nullptr; p.q = H(w.q); p.k = H(w.k); p.v = H(w.v);
-    if (int e = launch_gemm<128, EPI_QKV>(h, lm.a, lm.a, sw.m_qkv, p, stream, fr * 384 * C)) return e;
-  }
   }
   // attention -> o
   if (can_launch(h, MTTS_KIND_ATTN, 512.0 * w.B * (double)lc.L * lc.L)) {
@@ -1098,8 +1068,6 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
   if (const char* e = getenv("MTTS_NO_TMA_OUT")) h->tma_out = !(e[0] == '1');
   if (const char* e = getenv("MTTS_TAIL_PAIRS")) h->tail_pairs = (e[0] == '1');
   if (const char* e = getenv("MTTS_QKV_PAIRS")) h->qkv_pairs = (e[0] == '1');
-  if (const char* e = getenv("MTTS_GNBQKV")) h->fused_gnb = (e[0] == '1');
-  if (const char* e = getenv("MTTS_QKV_GEMM")) h->qkv_gemm = (e[0] == '1');
   build_tables(h);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
@@ -1120,10 +1088,9 @@ int mtts_create(const MttsConfig* cfg, int device, MttsHandle** out) {
     int e = 0;
     e |= set_gemm_pair_attr<EPI_STATS>(); e |= set_gemm_pair_attr<EPI_PLAIN>();
     e |= set_gemm_attr<256, EPI_STATS>(); e |= set_gemm_attr<256, EPI_PLAIN>();
-    e |= set_gemm_attr<128, EPI_QKV, 2>(); e |= set_gemm_attr<128, EPI_FINAL, 2>();
+    e |= set_gemm_attr<128, EPI_FINAL, 2>();
     if (cudaFuncSetAttribute(qkv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(qkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QKV_SMEM) != cudaSuccess) e = 1;
-    if (cudaFuncSetAttribute(gnb_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gn_apply2_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn2_smem_bytes<0, 64>()) != cudaSuccess) e = 1;
     if (cudaFuncSetAttribute(gn_apply2_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn2_smem_bytes<1, 64>()) != cudaSuccess) e = 1;

@@ -1,7 +1,7 @@
 // The QKV projection of the transformer blocks (reference model.py:662-664: to_q / to_k / to_v, no bias; 256 -> 3 x 128)
 // as its own tcgen05 kernel: q | k | v = a Wqkv^T for one 128-row tile per step of a persistent CTA.
 //
-// Through the generic gemm_tc_kernel<128, EPI_QKV> this GEMM ran at 410-550 TFLOP/s: K is only 256, so a (row tile, N
+// Through the generic gemm_tc_kernel (128-wide N tiles, removed since) this GEMM ran at 410-550 TFLOP/s: K is only 256, so a (row tile, N
 // tile) unit is 8 K16 steps long and the 64 KB activation tile was staged once for EACH of the three 128-wide N tiles.
 // Here a CTA owns whole row tiles: the `a` tile is staged ONCE (4 K-chunk tiles, double-buffered across row tiles), the
 // twelve 16 KB weight pieces stream through a ring, and the three 128-column accumulators rotate through FOUR tensor

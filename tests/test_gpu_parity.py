@@ -100,13 +100,10 @@ def test_against_reference_golden(case, golden, lj, vctk):
 # ---------------------------------------------------------------------------------------------
 # every intermediate of ONE estimator evaluation against the oracle trace (launch by launch)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("fused", [False, True], ids=["default", "MTTS_GNBQKV"])
-def test_estimator_stage_trace(fused, monkeypatch):
+def test_estimator_stage_trace():
     """Runs the estimator with a growing launch limit and compares each kernel's output buffer with the oracle's
     named intermediates (reference model.py:773-790 Block1D / ResnetBlock1D, :670-705 attention, :733-744 transformer
     block, :997-1043 level convs, :1045 final block): a wrong stage cannot hide behind the end-to-end tolerance."""
-    if fused:
-        monkeypatch.setenv("MTTS_GNBQKV", "1")          # read at handle creation
     dec, cfg, sd = U.make_decoder(160)
     dec.set_chains(1)                                   # one chain: the launch order is the stage order
     eng = dec._engine(torch.device("cuda", 0))
@@ -152,16 +149,11 @@ def test_estimator_stage_trace(fused, monkeypatch):
             cmp(pf + "res", buf("res", L, Lp, 256), trace[pf + "res"])
             run(base + 2); cmp(pf + "h1", buf("h1", L, Lp, 256), trace[pf + "h1"])           # GN-apply + Mish + temb
             run(base + 3); cmp(pf + "y2", buf("y", L, Lp, 256), trace[pf + "y.block2"])      # block2 conv
-            if fused:                                    # GN-apply + Mish + residual, LayerNorm1 (on chip), q | k | v: one launch
-                run(base + 4)
-                cmp(pf + "xr", buf("xr", L, Lp, 256), trace[pf + "xr"])
-                nl = 4
-            else:
-                run(base + 4)                            # GN-apply + Mish + residual, LayerNorm1
-                cmp(pf + "xr", buf("xr", L, Lp, 256), trace[pf + "xr"])
-                cmp(pf + "a", buf("a", L, Lp, 256), trace[pf + "a"].transpose(1, 2))
-                run(base + 5)                            # q | k | v (q pre-scaled by head_dim^-1/2)
-                nl = 5
+            run(base + 4)                                # GN-apply + Mish + residual, LayerNorm1
+            cmp(pf + "xr", buf("xr", L, Lp, 256), trace[pf + "xr"])
+            cmp(pf + "a", buf("a", L, Lp, 256), trace[pf + "a"].transpose(1, 2))
+            run(base + 5)                                # q | k | v (q pre-scaled by head_dim^-1/2)
+            nl = 5
             cmp(pf + "q", buf("q", L, Lp, 128), trace[pf + "q"].transpose(1, 2) * 0.125)
             cmp(pf + "k", buf("k", L, Lp, 128), trace[pf + "k"].transpose(1, 2))
             cmp(pf + "v", buf("v", L, Lp, 128), trace[pf + "v"].transpose(1, 2))
@@ -174,7 +166,7 @@ def test_estimator_stage_trace(fused, monkeypatch):
                 base += 1
         run(base + 2); cmp("hF", buf("h1", T, LpT, 256), trace["hF"])                        # final block
         out = run(-1)
-        assert dec.last_launch_count() == base + 3 == 6 + (43 if fused else 49)      # prologue + launches per evaluation
+        assert dec.last_launch_count() == base + 3 == 6 + 49      # prologue + launches per evaluation
         ma, rl = O.parity_errors(out.cpu(), ref, mask)
         assert ma <= O.TOL_MAX_ABS and rl <= EST_REL, (ma, rl)
     finally:
@@ -451,8 +443,8 @@ def test_chains_setting_keeps_results(lj):
 # opt-in kernel variants (environment switches read at handle creation) stay parity-green
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", ["MTTS_NO_PDL=1", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0", "MTTS_PAIRS=1,MTTS_PAIR_MIN_CHUNKS=0,MTTS_PAIR_TAP3=0",
-                                 "MTTS_PAIRS=0", "MTTS_TAIL_PAIRS=0", "MTTS_QKV_PAIRS=0", "MTTS_PAIRS=0,MTTS_TAIL_PAIRS=0,MTTS_QKV_PAIRS=0", "MTTS_NO_TAP3=1,MTTS_PAIRS=0", "MTTS_GNBQKV=1",
-                                 "MTTS_QKV_GEMM=1", "MTTS_GN_REGS=1", "MTTS_GN_BULK=1", "MTTS_NO_TMA_OUT=1", "MTTS_LANES=4"])
+                                 "MTTS_PAIRS=0", "MTTS_TAIL_PAIRS=0", "MTTS_QKV_PAIRS=0", "MTTS_PAIRS=0,MTTS_TAIL_PAIRS=0,MTTS_QKV_PAIRS=0", "MTTS_NO_TAP3=1,MTTS_PAIRS=0",
+                                 "MTTS_GN_REGS=1", "MTTS_GN_BULK=1", "MTTS_NO_TMA_OUT=1", "MTTS_LANES=4"])
 def test_opt_in_variants(env):
     """Every switch the library reads at handle creation, alone and in the combinations that select a
     different kernel, stays inside the parity bar."""
@@ -542,20 +534,6 @@ def test_current_device_is_preserved(lj):
         assert z.device == torch.device("cuda:1") and torch.cuda.current_device() == before
         ma, rl = O.parity_errors(z.cpu(), zr, mask)
         assert ma <= O.TOL_MAX_ABS and rl <= O.TOL_REL_L2, (ma, rl)
-
-
-def test_fused_gnb_qkv_equals_the_two_launch_path(lj, monkeypatch):
-    """gnb_qkv_kernel (MTTS_GNBQKV=1) executes the arithmetic of gn_apply_kernel<1> followed by the QKV GEMM in the same
-    order: the fused launch and the default two-launch path must agree to the last bit (multi-tile rows, utterance boundaries inside a warp's rows,
-    ragged masks, odd T)."""
-    dec, cfg, sd = lj
-    monkeypatch.setenv("MTTS_GNBQKV", "1")
-    dec2, _, _ = U.make_decoder(160)
-    for B, T, lengths, seed in [(3, 344, [344, 301, 222], 81), (5, 35, [35, 34, 9, 1, 20], 82), (2, 1024, None, 83)]:
-        mu, mask, z0, _ = O.make_inputs(cfg, B, T, lengths, seed=seed)
-        za = dec.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
-        zb = dec2.solve(_d(z0), _d(mu), _d(mask), 3, None, "euler", use_graph=False)
-        assert torch.equal(za, zb), (B, T, float((za - zb).abs().max()))
 
 
 def test_bulk_staged_groupnorm_pass_equals_the_register_staged_one(lj, monkeypatch):

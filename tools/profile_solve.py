@@ -12,7 +12,7 @@ from matcha_tts_b200 import Decoder, _lib  # noqa: E402
 
 # launches of one resnet + transformer stage, in order (switches as in mtts_create)
 NAMES = ["conv1"] + ([] if os.environ.get("MTTS_GNA_SPLIT") == "0" else ["gnA"]) + ["conv2"]
-NAMES += ["gnbqkv"] if os.environ.get("MTTS_GNBQKV") == "1" else ["gnB", "qkv"]
+NAMES += ["gnB", "qkv"]
 NAMES += ["attn", "tail"]
 
 
