@@ -637,6 +637,7 @@ def run_native(args):
 
     with torch.cuda.stream(stream):
         run_lanes(max(args.warmup, F * NSET))                   # captures the CUDA graph of every (lane, input set)
+        launches_per_step = lane_eng[0].launch_count()          # kernels of one solve as the timed region runs it (one chain per solve when F > 1)
         barrier()
         ev0, ev1 = run_lanes(args.steps)
         barrier()
