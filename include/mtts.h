@@ -113,6 +113,10 @@ int mtts_set_chains(MttsHandle* h, int n);
  * results are bit-identical for every value.  Takes effect for the following calls (cached graphs are dropped). */
 int mtts_set_lanes(MttsHandle* h, int lanes);
 
+/* The grid (CTAs) a persistent launch over `work_units` tiles gets under the current mtts_set_lanes value, for kernels with
+ * `ctas_per_sm` (1 or 2) resident CTAs per SM -- the rule above, exposed for tests and capacity planning. */
+int mtts_debug_lane_grid(const MttsHandle* h, int work_units, int ctas_per_sm);
+
 /* Number of kernels enqueued by the last estimator_forward / euler_solve call on this handle. */
 int mtts_last_launch_count(const MttsHandle* h);
 

@@ -58,6 +58,7 @@ SIGNATURES = {
                                                                      C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mtts_set_chains": (C.c_int, [C.c_void_p, C.c_int]),
     "mtts_set_lanes": (C.c_int, [C.c_void_p, C.c_int]),
+    "mtts_debug_lane_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mtts_release_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mtts_last_launch_count": (C.c_int, [C.c_void_p]),
     "mtts_debug_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),

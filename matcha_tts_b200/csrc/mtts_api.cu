@@ -1375,6 +1375,11 @@ int mtts_set_lanes(MttsHandle* h, int lanes) {
   return 0;
 }
 
+int mtts_debug_lane_grid(const MttsHandle* h, int work_units, int ctas_per_sm) {
+  if (!h || work_units < 0 || ctas_per_sm < 1 || ctas_per_sm > 2) return MTTS_EINVAL;
+  return lane_grid(h, work_units, ctas_per_sm);
+}
+
 int mtts_last_launch_count(const MttsHandle* h) { return h ? h->launch_count : 0; }
 
 int mtts_debug_profile_begin(MttsHandle* h, void* stream) {

@@ -48,6 +48,25 @@ def test_lanes_and_chains_switches_validate_their_argument(libmtts):
             assert libmtts.mtts_set_lanes(h, n) < 0
         assert libmtts.mtts_set_lanes(None, 2) < 0
         assert libmtts.mtts_set_chains(h, 9) < 0 and libmtts.mtts_set_chains(h, 1) == 0
+        # the SM share of a persistent launch (148 SMs assumed without a device): all SMs for one solve at a time; with n
+        # lanes the grid with the least wave-quantisation waste inside [148 / n, 148 * 5/4 / n]
+        grid = libmtts.mtts_debug_lane_grid
+        _lib.check(libmtts.mtts_set_lanes(h, 1))
+        assert [grid(h, t, 1) for t in (0, 3, 148, 173, 692)] == [0, 3, 148, 148, 148] and grid(h, 384, 2) == 296
+        _lib.check(libmtts.mtts_set_lanes(h, 4))
+        assert grid(h, 173, 1) == 44 and grid(h, 87, 1) == 44          # 4 and 2 full waves (43 CTAs would need 5 and 3)
+        assert grid(h, 30, 1) == 30 and grid(h, 37, 1) == 37            # fewer tiles than the share: one CTA each
+        assert grid(h, 257, 1) == 43 and grid(h, 129, 1) == 43          # B16 x T2048: 6 and 3 full waves
+        assert 74 <= grid(h, 384, 2) <= 93                              # two CTAs per SM: a share of 296
+        _lib.check(libmtts.mtts_set_lanes(h, 5))
+        assert grid(h, 173, 1) == 35 and 30 <= grid(h, 87, 1) <= 37
+        for lanes in (2, 3, 6, 8, 16):
+            _lib.check(libmtts.mtts_set_lanes(h, lanes))
+            for tiles in (1, 44, 87, 173, 346, 692, 5000):
+                g = grid(h, tiles, 1)
+                lo, hi = -(-148 // lanes), -(-(148 * 5 // 4) // lanes)
+                assert (g == tiles and tiles <= lo) or lo <= g <= hi, (lanes, tiles, g)
+        assert grid(None, 4, 1) < 0 and grid(h, 4, 3) < 0
     finally:
         libmtts.mtts_destroy(h)
 
