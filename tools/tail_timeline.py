@@ -1,5 +1,6 @@
 """Phase timeline of ff_tail_kernel (first tile of CTA 0 and the mean over CTAs), from clock64 stamps.
-python tools/tail_timeline.py [B T stage_limit]  -- runs the estimator up to the first tail launch of stage 1 (level T/2)"""
+python tools/tail_timeline.py [B T stage_limit]  -- runs the estimator up to the tail launch of stage 0 (level T; 6 + 7 launches).
+With CTA pairs (the default) the stamps come from the pair leaders, one row per 256-row unit."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ from matcha_tts_b200 import Decoder, _lib  # noqa: E402
 
 def main():
     B, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 344)
-    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 6 + 7 + 1 + 7      # prologue + stage 0 + down conv + stage 1
+    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 6 + 7      # prologue + stage 0 (its tail is the only tail launch)
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     dec = Decoder(160, 80, num_heads=2).to(dev)
@@ -40,12 +41,13 @@ def main():
         _lib.check(eng.lib.mtts_debug_set_launch_limit(eng.h, -1))
         _lib.check(eng.lib.mtts_debug_set_tail_timeline(eng.h, None))
     tl = buf.cpu().double()
-    used = tl[:, 0] != 0
+    used = (tl[:, 0] != 0) & (tl[:, 64] != 0)
     n = int(used.sum())
     a = tl[used]
     t0 = a[:, 0:1]                                 # MMA: r_empty passed
-    rel = (a - t0) / 1.85e3                        # us at ~1.85 GHz
-    m = rel.mean(0)
+    rel = (a - t0) / 1.965e3                       # us at 1.965 GHz
+    rel[a == 0] = float("nan")
+    m = torch.nanmean(rel, dim=0)
     print(f"{n} CTAs recorded (launch limit {limit}); times in us since the MMA thread entered the tile (mean over CTAs)")
     print(f"MMA : to_out issued {m[1]:.2f}   c_ready seen {m[2]:.2f}")
     print(f"EPI : r_full seen {m[64]:.2f}   c_ready arrive {m[65]:.2f}   r_done seen {m[66]:.2f}   r_empty arrive {m[67]:.2f}")
