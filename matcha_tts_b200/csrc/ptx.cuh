@@ -446,11 +446,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 // same, saturating at the fp16 range: used for the FF1/SnakeBeta intermediate, the only tensor whose magnitude is not
 // bounded by a normalisation layer (with trained weights an overflow would otherwise poison the row with inf/NaN)
+// One F2FP with .satfinite instead of two FMNMX per element + F2FP: this sits in the SnakeBeta pass of the fused tail, whose
+// issue rate sets the period of the FF loop (profiles/r06_tail_c_in_smem_experiment.txt).  a -> low half, b -> high half.
 __device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
