@@ -78,6 +78,16 @@ constexpr int TAIL_OFF_RED = TAIL_OFF_PAR + TAIL_PAR_FLOATS * 4;      // LayerNo
 constexpr int TAIL_OFF_BAR = TAIL_OFF_RED + 128 * TAIL_NCG * 8;
 constexpr int TAIL_SMEM = TAIL_OFF_BAR + 256;
 static_assert(TAIL_SMEM <= 232448, "exceeds the 227 KB of shared memory one CTA can own");
+// CTA pairs (CG = 2) stage half of every weight piece, so their ring needs 4 x 16 KB, not 4 x 32 KB.  The 64 KB that frees
+// hold c = LayerNorm3(x_a) in SHARED memory (four 128B-swizzled K tiles, the A operand of FF1 like any other): an MMA whose
+// A operand comes from tensor memory costs ~40 cycles more than its 64-cycle floor (104 cycles per K16 step at N = 128) --
+// and the 128 tensor-memory columns c occupied become a SECOND FF1 accumulator, so FF1 of chunk j + 1 no longer waits for
+// the epilogue to pick up chunk j.  The `o` tile of the next row tile lands in the first half of the same region (it is
+// dead once to_out has completed, and c is dead once the last FF1 has).
+constexpr int TAIL2_OFF_C = TAIL_OFF_RING;                              // 64 KB: c (4 K tiles of 16 KB); o (2 K tiles) before it
+constexpr int TAIL2_OFF_RING = TAIL2_OFF_C + 65536;                     // 4 x 16 KB
+constexpr int TAIL2_PIECE = TAIL_PIECE / 2;
+static_assert(TAIL2_OFF_RING + TAIL_NST * TAIL2_PIECE <= TAIL_OFF_PAR, "the pair layout fits the single-CTA ring region");
 
 template <int CG>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
@@ -110,7 +120,9 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
   uint64_t* r_done = r_full + 12;                   // all FF2 MMAs of the tile complete
   uint64_t* r_empty = r_full + 13;                  // epilogue has read the final accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 14);
-  static_assert((2 * TAIL_NST + 15) * 8 <= 256, "barrier block");
+  uint64_t* o_full = r_full + 15;                   // CG == 2: the o tile has landed in the c region
+  uint64_t* c_free = r_full + 16;                   // CG == 2: the last FF1 of the tile has read c (the next o tile may land)
+  static_assert((2 * TAIL_NST + 17) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!p.pdl_late) pdl_launch_dependents();   // late: when the CTA's last tile reaches its final epilogue (see gemm_tc.cuh)
@@ -123,6 +135,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], CG * NEW); }
     for (int i = 0; i < TAIL_NSB; ++i) { mbar_init(&s_ready[i], CG * NEW); mbar_init(&s_empty[i], 1); }
     mbar_init(r_done, 1); mbar_init(r_empty, CG * NEW);
+    mbar_init(o_full, 1); mbar_init(c_free, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmO3); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1_3); tma_prefetch_desc(&tmW2);
   }
@@ -146,8 +159,8 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
   }
   const uint32_t tR = tmem_base;
-  const uint32_t tD1 = tmem_base + 256;
-  const uint32_t tC = tmem_base + 384;
+  const uint32_t tD1 = tmem_base + 256;   // CG == 2: two FF1 accumulators, columns [256, 384) and [384, 512)
+  const uint32_t tC = tmem_base + 384;    // CG == 1: c as packed fp16 pairs
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -156,6 +169,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       uint32_t it = 0;  // running ring item counter
       const uint64_t pol = l2_policy_evict_last();
       constexpr uint32_t WBYTES = TAIL_PIECE / CG;   // this CTA's share of a weight piece
+      constexpr int R_OFF = (CG == 2) ? TAIL2_OFF_RING : TAIL_OFF_RING, R_PIECE = (CG == 2) ? TAIL2_PIECE : TAIL_PIECE;
       auto slot_acquire = [&]() -> uint32_t {
         const uint32_t slot = it % TAIL_NST, use = it / TAIL_NST;
         mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
@@ -167,7 +181,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
       auto put2 = [&](const CUtensorMap* tm, int c0) {  // weights: this CTA's 256 / CG output rows x 64 cols
         const uint32_t slot = slot_acquire();
         if (elect_one()) {
-          uint8_t* dst = smem + TAIL_OFF_RING + slot * TAIL_PIECE;
+          uint8_t* dst = smem + R_OFF + slot * R_PIECE;
           if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * WBYTES);
           if constexpr (CG == 2) {
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[slot]), 0);
@@ -184,7 +198,7 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t slot = slot_acquire();
           if (elect_one()) {
-            uint8_t* dst = smem + TAIL_OFF_RING + slot * TAIL_PIECE;
+            uint8_t* dst = smem + R_OFF + slot * R_PIECE;
             if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * WBYTES);
             if constexpr (CG == 2) {
               const uint32_t lbar = mapa_u32(smem_u32(&full_bar[slot]), 0);
@@ -199,17 +213,24 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         }
       };
       bool first = true;
-      for (int unit = unit0; unit < m_units; unit += nunits) {
+      uint32_t n_tile_p = 0;
+      for (int unit = unit0; unit < m_units; unit += nunits, ++n_tile_p) {
         const int tile = CG * unit + (int)crank;   // CG == 2: may be == m_tiles on the last unit (rows out of range load as zeros)
         put2(&tmWo, 0);    // Wo K-chunk 0
         put2(&tmWo, 64);   // Wo K-chunk 1
         if (first) { pdl_wait(); first = false; }  // o is the first operand produced by the previous kernel
-        {
+        if constexpr (CG == 2) {   // the o tile goes to the first half of the c region, free once the previous tile's last FF1 has read c
+          mbar_wait(c_free, (n_tile_p & 1) ^ 1);
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(o_full, CG * TAIL_PIECE);   // each CTA loads its own row tile of o
+            tma_load_3d_pair(smem + TAIL2_OFF_C, &tmO3, mapa_u32(smem_u32(o_full), 0), 0, tile * 128, 0);
+          }
+          __syncwarp();
+        } else {
           const uint32_t slot = slot_acquire();
           if (elect_one()) {
-            if (crank == 0) mbar_arrive_expect_tx(&full_bar[slot], CG * TAIL_PIECE);   // each CTA loads its own row tile of o
-            if constexpr (CG == 2) tma_load_3d_pair(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, mapa_u32(smem_u32(&full_bar[slot]), 0), 0, tile * 128, 0);
-            else tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, &full_bar[slot], 0, tile * 128, 0);
+            mbar_arrive_expect_tx(&full_bar[slot], TAIL_PIECE);
+            tma_load_3d(smem + TAIL_OFF_RING + slot * TAIL_PIECE, &tmO3, &full_bar[slot], 0, tile * 128, 0);
           }
           __syncwarp();
         }
@@ -238,19 +259,22 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
     auto commit = [](uint64_t* bar) {   // CG == 2: arrives on the barrier at this offset in BOTH CTAs
       if constexpr (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
     };
-    const uint32_t ring = smem_u32(smem + TAIL_OFF_RING);
+    const uint32_t ring = smem_u32(smem + ((CG == 2) ? TAIL2_OFF_RING : TAIL_OFF_RING));
     const uint32_t sbuf = smem_u32(smem + TAIL_OFF_S);
+    const uint32_t cbuf = smem_u32(smem + TAIL2_OFF_C);   // CG == 2
     auto slot_wait = [&](uint32_t item) -> uint32_t {
       const uint32_t slot = item % TAIL_NST, use = item / TAIL_NST;
       mbar_wait(&full_bar[slot], use & 1);
       tc_fence_after();
-      return ring + slot * TAIL_PIECE;
+      return ring + slot * ((CG == 2) ? TAIL2_PIECE : TAIL_PIECE);
     };
     // ring items of one tile (two per chunk operand): 0,1 Wo K-chunks | 2 o | W1_0 (3,4) W1_1 (5,6) | then for j = 0..7:
     // W2_j (2 items), W1_{j+2} (2 items, while it exists)
-    auto item_w1 = [](int k) -> uint32_t { return k < 2 ? 3u + 2u * k : 4u * k + 1u; };          // first of two
-    auto item_w2 = [](int j) -> uint32_t { return j <= 5 ? 7u + 4u * j : 31u + 2u * (j - 6); };  // first of two
-    constexpr uint32_t ITEMS = 35;
+    // (CG == 2: the o tile is not a ring item -- it has its own region and barrier -- so everything after it moves down by one)
+    constexpr uint32_t OI = (CG == 2) ? 0u : 1u;
+    auto item_w1 = [](int k) -> uint32_t { return (k < 2 ? 3u + 2u * k : 4u * k + 1u) - (1u - OI); };          // first of two
+    auto item_w2 = [](int j) -> uint32_t { return (j <= 5 ? 7u + 4u * j : 31u + 2u * (j - 6)) - (1u - OI); };  // first of two
+    constexpr uint32_t ITEMS = 34 + OI;
     long long* tl = (p.tl != nullptr) ? p.tl + (size_t)unit0 * 128 : nullptr;
     uint32_t n_tile = 0;
     if (warp == 1) {
@@ -263,7 +287,9 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tc_fence_after();
         if (tl && lane == 0) tl[0] = clock64();
         {
-          const uint32_t a = slot_wait(base + 2);
+          uint32_t a;
+          if constexpr (CG == 2) { mbar_wait(o_full, n_tile & 1); tc_fence_after(); a = cbuf; }
+          else a = slot_wait(base + 2);
           for (int k = 0; k < 2; ++k) {
             const uint32_t b = slot_wait(base + k);
             const uint64_t da = umma_desc_sw128(a + k * 16384), db = umma_desc_sw128(b);
@@ -271,7 +297,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) mma_ss(tR, da + 2 * kk, db + 2 * kk, idesc256, (k | kk) != 0);
               commit(&empty_bar[(base + k) % TAIL_NST]);
-              if (k == 1) { commit(&empty_bar[(base + 2) % TAIL_NST]); commit(r_full); }
+              if (k == 1) {
+                if constexpr (CG == 1) commit(&empty_bar[(base + 2) % TAIL_NST]);
+                commit(r_full);
+              }
             }
             __syncwarp();
           }
@@ -282,7 +311,9 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tc_fence_after();
         if (tl && lane == 0) tl[2] = clock64();
         for (int j = 0; j < TAIL_NJ; ++j) {
-          mbar_wait(&d1_empty[0], (n_d1e & 1) ^ 1);
+          // CG == 2: two FF1 accumulators (chunk parity); CG == 1: one.  n_d1e counts the chunks issued so far.
+          const uint32_t db_i = (CG == 2) ? (n_d1e & 1u) : 0u, use = (CG == 2) ? (n_d1e >> 1) : n_d1e;
+          mbar_wait(&d1_empty[db_i], (use & 1) ^ 1);
           ++n_d1e;
           tc_fence_after();
           if (tl && lane == 0 && j < 8) tl[4 + 4 * j] = clock64();
@@ -294,10 +325,18 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
 #pragma unroll
               for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // A: 8 TMEM columns per K16 step; B: this CTA's 128 / CG hidden units x 64 per K-chunk (16 / CG KB)
-                  mma_ts(tD1, tC + (2 * hh + sub) * 32 + kk * 8, db0 + sub * ((16384 / CG) >> 4) + 2 * kk, idesc128, (hh | sub | kk) != 0);
+                for (int kk = 0; kk < 4; ++kk) {  // B: this CTA's 128 / CG hidden units x 64 per K-chunk (16 / CG KB)
+                  if constexpr (CG == 2)          // A: c from shared memory, K tile 2 hh + sub
+                    mma_ss(tD1 + db_i * 128, umma_desc_sw128(cbuf + (2 * hh + sub) * 16384) + 2 * kk, db0 + sub * ((16384 / CG) >> 4) + 2 * kk,
+                           idesc128, (hh | sub | kk) != 0);
+                  else                            // A: 8 TMEM columns per K16 step
+                    mma_ts(tD1, tC + (2 * hh + sub) * 32 + kk * 8, db0 + sub * ((16384 / CG) >> 4) + 2 * kk, idesc128, (hh | sub | kk) != 0);
+                }
               commit(&empty_bar[item % TAIL_NST]);
-              if (hh == 1) commit(&d1_full[0]);
+              if (hh == 1) {
+                commit(&d1_full[db_i]);
+                if (CG == 2 && j == TAIL_NJ - 1) commit(c_free);   // c has been read: the next tile's o may land
+              }
             }
             __syncwarp();
           }
@@ -418,9 +457,17 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
           uint32_t pk[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) pk[u] = pack_h2(v[2 * u], v[2 * u + 1]);
-          tmem_st16(tC + lane_off + (col >> 1), pk);  // c as fp16 pairs: A operand of FF1, read from TMEM
+          if constexpr (CG == 2) {   // c into shared memory: K tile col / 64, 16-byte units (col % 64) / 8 .. + 4 of the row (128B swizzle)
+            const uint32_t crow = smem_u32(smem + TAIL2_OFF_C) + (col >> 6) * 16384 + trow * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sts128(crow + (((((col & 63) >> 3) + u) ^ (trow & 7)) << 4), make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]));
+          } else {
+            tmem_st16(tC + lane_off + (col >> 1), pk);  // c as fp16 pairs: A operand of FF1, read from TMEM
+          }
         }
-        tmem_st_wait();
+        if constexpr (CG == 2) fence_proxy_async_smem();
+        else tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(c_ready);
@@ -430,9 +477,10 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
 #pragma unroll 1
       for (int j = 0; j < TAIL_NJ; ++j) {
         const uint32_t sb = n_s % TAIL_NSB;  // s buffer
+        const uint32_t db_i = (CG == 2) ? (n_d1f[0] & 1u) : 0u, d1use = (CG == 2) ? (n_d1f[0] >> 1) : n_d1f[0];   // n_d1f[0]: chunks so far
         if (lane == 0) {
           mbar_wait(&s_empty[sb], ((n_s / TAIL_NSB) & 1) ^ 1);  // FF2_{j-2} no longer reads S[sb]
-          mbar_wait(&d1_full[0], n_d1f[0] & 1);
+          mbar_wait(&d1_full[db_i], d1use & 1);
         }
         ++n_s;
         ++n_d1f[0];
@@ -440,11 +488,11 @@ ff_tail_kernel(const __grid_constant__ CUtensorMap tmO3, const __grid_constant__
         tc_fence_after();
         if (tl && j < 8) tl[4 + 2 * j] = clock64();
         float v[32];
-        tmem_ld32(tD1 + lane_off + cg * 32, v);
+        tmem_ld32(tD1 + db_i * 128 + lane_off + cg * 32, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_leader(&d1_empty[0]);  // the accumulator chunk is in registers: FF1_{j+1} may overwrite it
+        if (lane == 0) arrive_leader(&d1_empty[db_i]);  // the accumulator chunk is in registers: FF1_{j+1 / j+2} may overwrite it
         const uint32_t pb = spar + (1024 + j * 128 + cg * 32) * 4;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
