@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round artefacts on one B200 (run under gpurun; writes gpurun_out/<tag>_*): tools/collect_profiles.sh <tag>
-tag=${1:-r05x}
+tag=${1:-r06z}
 o=gpurun_out
 python -m pytest tests -m gpu -x -q > $o/${tag}_gpu_tests.txt 2>&1; tail -2 $o/${tag}_gpu_tests.txt
 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err
