@@ -27,7 +27,7 @@
 //   FF1_0 | FF1_1 FF2_0 | FF1_2 FF2_1 | ... | FF1_7 FF2_6 | FF2_7
 // so that the tensor pipe works on FF1_{j+1} and FF2_{j-1} while the epilogue warps apply SnakeBeta to chunk j.
 //
-// CG = 2 is the CTA-pair variant (same maths, same TMEM / shared-memory plan per CTA): a cluster of two CTAs works on two
+// CG = 2 (the default) is the CTA-pair variant (same maths; its own TMEM / shared-memory plan, see TAIL2_* below): a cluster of two CTAs works on two
 // consecutive 128-row tiles with tcgen05 cta_group::2 MMAs (M = 256).  Each CTA stages only ITS HALF of every weight
 // piece (Wo / W2: 128 of the 256 output rows, W1: 64 of the chunk's 128 hidden units; the tensor maps have half-size
 // boxes), so the shared-memory traffic of the FF loop -- the bound of the single-CTA kernel --
